@@ -1,0 +1,278 @@
+/*
+ * p2v.h — C ABI of the B200-native batch Plonky2 verifier (libp2v.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of bkomuves/plonky2-verifier:
+ * batch proof verification (Poseidon/Merkle -> Fiat-Shamir challenger -> constraint
+ * check at zeta -> FRI check).  The reference has no FFI of its own (it is pure
+ * Haskell); every entry point below names the pure Haskell function it replaces
+ * (file:line relative to the reference's src/), i.e. the function a
+ * `foreign import ccall` shim would wrap.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *  - field elements are uint64_t.  Inputs may be any u64 (they are reduced mod
+ *    p = 2^64-2^32+1 exactly like `mkGoldilocks`, Algebra/Goldilocks.hs:132);
+ *    every output is the canonical representative in [0,p);
+ *  - every data pointer may be a HOST pointer or a DEVICE pointer of the context's
+ *    GPU; the library detects which (cudaPointerGetAttributes) and stages host
+ *    buffers through the context's stream;
+ *  - "SoA [k][n]" means k planes of n contiguous elements: element (j, i) is at
+ *    ptr[j*n + i];
+ *  - return value: 0 on success, a negative P2V_E_* code otherwise;
+ *    p2v_last_error() gives the message.  No exception crosses the boundary;
+ *  - one CUDA stream per context; calls on one context are serialised, different
+ *    contexts may be used from different threads;
+ *  - there is NO CPU fallback: without a usable sm_100 GPU p2v_ctx_create fails.
+ */
+#ifndef P2V_H
+#define P2V_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P2V_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------ */
+#define P2V_OK 0
+#define P2V_E_INVALID (-1)  /* bad argument                                       */
+#define P2V_E_CUDA (-2)     /* CUDA runtime error (message in p2v_last_error)      */
+#define P2V_E_NOGPU (-3)    /* no usable GPU: there is no CPU fallback             */
+#define P2V_E_PARSE (-4)    /* malformed JSON / gate string                        */
+#define P2V_E_SHAPE (-5)    /* input does not have the circuit's shape             */
+#define P2V_E_UNSUPPORTED (-6) /* reference `error` sites for unsupported features */
+#define P2V_E_NOMEM (-7)
+
+/* ---- limits of the fixed-size shape record ----------------------------------- */
+#define P2V_MAX_GATES 32
+#define P2V_MAX_GROUPS 8
+#define P2V_MAX_ROUTED 128
+#define P2V_MAX_STEPS 8
+#define P2V_MAX_LUTS 8
+#define P2V_MAX_WEIGHTS 64
+
+/* Gate kinds: the constructors of `data Gate`, Gate/Base.hs:27-45. */
+enum p2v_gate_kind {
+  P2V_GATE_ARITHMETIC = 0,      /* p0 = num_ops                                   */
+  P2V_GATE_ARITHMETIC_EXT = 1,  /* p0 = num_ops                                   */
+  P2V_GATE_BASE_SUM = 2,        /* p0 = num_limbs, p1 = base                      */
+  P2V_GATE_COSET_INTERP = 3,    /* p0 = subgroup_bits, p1 = degree, weights       */
+  P2V_GATE_CONSTANT = 4,        /* p0 = num_consts                                */
+  P2V_GATE_EXPONENTIATION = 5,  /* p0 = num_power_bits                            */
+  P2V_GATE_LOOKUP = 6,          /* p0 = num_slots                                 */
+  P2V_GATE_LOOKUP_TABLE = 7,    /* p0 = num_slots, p1 = last_lut_row              */
+  P2V_GATE_MUL_EXT = 8,         /* p0 = num_ops                                   */
+  P2V_GATE_NOOP = 9,
+  P2V_GATE_PUBLIC_INPUT = 10,
+  P2V_GATE_POSEIDON = 11,       /* p0 = width (12)                                */
+  P2V_GATE_POSEIDON_MDS = 12,   /* p0 = width (12)                                */
+  P2V_GATE_RANDOM_ACCESS = 13,  /* p0 = bits, p1 = num_copies, p2 = num_extra_constants */
+  P2V_GATE_REDUCING = 14,       /* p0 = num_coeffs                                */
+  P2V_GATE_REDUCING_EXT = 15,   /* p0 = num_coeffs                                */
+  P2V_GATE_UNKNOWN = 16
+};
+
+typedef struct p2v_gate {
+  int32_t kind;            /* enum p2v_gate_kind                                  */
+  int32_t p0, p1, p2;      /* parameters, see above                               */
+  int32_t group;           /* selector_indices[k]      (Types.hs:97-101)          */
+  int32_t num_constraints; /* length of the gate's committed constraint list      */
+  int32_t weights_off;     /* CosetInterpolationGate: first weight in `weights`   */
+  int32_t weights_len;
+} p2v_gate;
+
+/*
+ * p2v_shape — everything `CommonCircuitData` (Types.hs:47-70) says about a circuit,
+ * flattened to a POD.  A batch is shape-homogeneous.
+ */
+typedef struct p2v_shape {
+  /* CircuitConfig, Types.hs:73-87 */
+  int32_t num_wires;
+  int32_t num_routed_wires;
+  int32_t num_gate_constants; /* config_num_constants                            */
+  int32_t num_challenges;
+  /* FriConfig / FriParams, Types.hs:116-173 */
+  int32_t degree_bits;
+  int32_t rate_bits;
+  int32_t cap_height;
+  int32_t pow_bits;
+  int32_t num_queries;
+  int32_t num_steps;                       /* expandReductionStrategy, Plonk/FRI.hs:337-354 */
+  int32_t step_arity_bits[P2V_MAX_STEPS];
+  int32_t final_poly_len;                  /* 2^(degree_bits - sum(arity_bits))   */
+  /* CommonCircuitData */
+  int32_t quotient_degree_factor;
+  int32_t num_constants;                   /* all constant columns                */
+  int32_t num_public_inputs;
+  int32_t num_partial_products;
+  int32_t num_lookup_polys;
+  int32_t num_lookup_selectors;
+  int32_t num_gates;
+  int32_t num_groups;
+  int32_t group_start[P2V_MAX_GROUPS];
+  int32_t group_end[P2V_MAX_GROUPS];
+  p2v_gate gates[P2V_MAX_GATES];
+  int32_t num_weights;
+  uint64_t weights[P2V_MAX_WEIGHTS];       /* barycentric weights of all CosetInterpolation gates */
+  uint64_t k_is[P2V_MAX_ROUTED];
+  /* lookup tables, Types.hs:28-36: lut k = pairs lut_pairs[2*lut_off[k] .. 2*lut_off[k+1]) as (inp,out) */
+  int32_t num_luts;
+  int32_t lut_off[P2V_MAX_LUTS + 1];
+  const uint64_t *lut_pairs;               /* owned by whoever built the shape    */
+} p2v_shape;
+
+/*
+ * p2v_layout — the flat u64 "proof blob" a shape implies: the fields of
+ * ProofWithPublicInputs (Types.hs:251-279) in declaration order.
+ *
+ *   proof part (per proof), word offsets:
+ *     wires_cap | zs_pp_cap | quotient_cap                    each 4*2^cap_height
+ *     openings: constants, plonk_sigmas, wires, plonk_zs, plonk_zs_next,
+ *               partial_products, quotient_polys, lookup_zs, lookup_zs_next   (2 words per FExt)
+ *     commit_phase_merkle_caps[num_steps]                      each 4*2^cap_height
+ *     final_poly (2*final_poly_len) | pow_witness (1) | public_inputs
+ *   then num_queries query parts of `query_words` words each:
+ *     for oracle o in constants,witness,zs_pp_lookup,quotient:  leaf[width_o] | siblings[4*init_path_len]
+ *     for step s: evals[2*2^arity_s] | siblings[4*step_path_len[s]]
+ */
+typedef struct p2v_layout {
+  int32_t cap_words;
+  int32_t off_wires_cap, off_zs_pp_cap, off_quotient_cap;
+  int32_t off_open_constants, off_open_sigmas, off_open_wires, off_open_zs, off_open_zs_next;
+  int32_t off_open_pp, off_open_quotient, off_open_lookup_zs, off_open_lookup_zs_next;
+  int32_t n_open_constants, n_open_sigmas, n_open_wires, n_open_zs, n_open_zs_next;
+  int32_t n_open_pp, n_open_quotient, n_open_lookup_zs, n_open_lookup_zs_next;
+  int32_t off_commit_caps, off_final_poly, off_pow_witness, off_public_inputs;
+  int32_t proof_words;                 /* size of the per-proof part                */
+  int32_t oracle_width[4];             /* oracleWidths, Plonk/FRI.hs:56-65          */
+  int32_t init_path_len;               /* degree_bits + rate_bits - cap_height      */
+  int32_t q_off_leaf[4], q_off_sibs[4];
+  int32_t q_off_step_evals[P2V_MAX_STEPS], q_off_step_sibs[P2V_MAX_STEPS];
+  int32_t step_path_len[P2V_MAX_STEPS];
+  int32_t query_words;                 /* size of one query part                    */
+  int32_t blob_words;                  /* proof_words + num_queries*query_words     */
+  int32_t vkey_words;                  /* 4*2^cap_height + 4 (cap, circuit_digest)  */
+} p2v_layout;
+
+/*
+ * Per-proof verdict.  status word = code | (query << 8) | (detail << 16).
+ * The accept bit of a proof is (code == P2V_ST_ACCEPT).  Codes >= 16 are the reference's
+ * `error` sites (imprecise exceptions); codes 1..3 are `False`.
+ */
+enum p2v_status_code {
+  P2V_ST_ACCEPT = 0,
+  P2V_ST_FALSE_EQS = 1,    /* checkCombinedPlonkEquations False (Plonk/Verifier.hs:62-64); detail = mask of failing rounds */
+  P2V_ST_FALSE_POW = 2,    /* checkProofOfWork False (Plonk/FRI.hs:212-216)        */
+  P2V_ST_FALSE_FINAL = 3,  /* final_poly_eval /= folded (Plonk/FRI.hs:407); query  */
+  P2V_ST_ERR_INIT_MERKLE = 16, /* Plonk/FRI.hs:108; query, detail = mask of failing oracles */
+  P2V_ST_ERR_STEP_MERKLE = 17, /* Plonk/FRI.hs:310; query, detail = step           */
+  P2V_ST_ERR_STEP_EVAL = 18    /* Plonk/FRI.hs:311; query, detail = step           */
+};
+
+/* Challenges of one proof, SoA [p2v_challenges_words(shape)][n]; order (Challenge/Verifier.hs:45-53,
+ * Challenge/FRI.hs:24-30): betas[r], gammas[r], alphas[r], deltas[4r or 0], zeta[2], fri_alpha[2],
+ * fri_betas[2*num_steps], pow_response[1], query_indices[num_queries]. */
+
+typedef struct p2v_ctx p2v_ctx;
+typedef struct p2v_circuit p2v_circuit;
+
+/* ---- context ----------------------------------------------------------------- */
+int p2v_abi_version(void);
+int p2v_ctx_create(int device, p2v_ctx **out);
+void p2v_ctx_destroy(p2v_ctx *ctx);
+const char *p2v_last_error(const p2v_ctx *ctx); /* ctx may be NULL: last error of this thread */
+void *p2v_ctx_stream(p2v_ctx *ctx);              /* the context's cudaStream_t                 */
+int p2v_ctx_sync(p2v_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t p2v_ctx_launch_count(const p2v_ctx *ctx);
+/* pinned host memory for callers that want asynchronous staging */
+int p2v_host_alloc(size_t bytes, void **out);
+void p2v_host_free(void *p);
+
+/* ---- L2 Hash ------------------------------------------------------------------ */
+/* `permutation :: State -> State`, Hash/Poseidon.hs:42-46.  in/out SoA [12][n]. */
+int p2v_poseidon_permute(p2v_ctx *ctx, const uint64_t *in, uint64_t *out, size_t n);
+/* `sponge :: [F] -> Digest`, Hash/Sponge.hs:26-31.  leaves SoA [w][n] -> digests SoA [4][n]. */
+int p2v_hash_leaves(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, size_t n, uint64_t *digests);
+/* `compress :: Digest -> Digest -> Digest`, Hash/Merkle.hs:21-23.  SoA [4][n] each. */
+int p2v_compress(p2v_ctx *ctx, const uint64_t *left, const uint64_t *right, uint64_t *out, size_t n);
+/* `checkMerkleProof cap idx leaf proof`, Hash/Merkle.hs:27-42, for n openings against ONE cap.
+ *   leaves SoA [w][n]; idx [n]; siblings SoA [path_len*4][n] (sibling l, word k at plane l*4+k);
+ *   cap [2^cap_height][4] row-major; ok_bits: ceil(n/32) words, bit i%32 of word i/32;
+ *   roots_out (optional, may be NULL) SoA [4][n] = the reconstructed cap entry. */
+int p2v_merkle_verify(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, const uint32_t *idx,
+                      const uint64_t *siblings, uint32_t path_len, const uint64_t *cap,
+                      uint32_t cap_height, size_t n, uint32_t *ok_bits, uint64_t *roots_out);
+/* Build a Poseidon Merkle tree over 2^log_n leaves (SoA [w][2^log_n]); the prover-side dual of
+ * Hash/Merkle.hs used to make synthetic trees.  digests_out: SoA levels, level 0 = leaf digests
+ * [4][2^log_n], level l = [4][2^(log_n-l)], concatenated up to and including the cap level
+ * (log_n - cap_height); total 4*(2^(log_n+1) - 2^cap_height) words. */
+int p2v_merkle_build(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, uint32_t log_n,
+                     uint32_t cap_height, uint64_t *digests_out);
+/* Gather n openings from a tree built by p2v_merkle_build: leaves_out SoA [w][n],
+ * siblings_out SoA [(log_n-cap_height)*4][n], cap_out [2^cap_height][4]. */
+int p2v_merkle_open(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, uint32_t log_n,
+                    uint32_t cap_height, const uint64_t *digests, const uint32_t *idx, size_t n,
+                    uint64_t *leaves_out, uint64_t *siblings_out, uint64_t *cap_out);
+
+/* ---- host side: JSON wire format (Types.hs:47-279, Gate/Parser.hs:107-240) ---- */
+/* `FromJSON CommonCircuitData`.  On success *out is filled; free with p2v_shape_free. */
+int p2v_parse_common(const char *json, size_t len, p2v_shape *out);
+void p2v_shape_free(p2v_shape *shape);
+/* `recognizeGate`, Gate/Parser.hs:107.  weights: out array of P2V_MAX_WEIGHTS. */
+int p2v_parse_gate(const char *str, size_t len, p2v_gate *out, uint64_t *weights);
+int p2v_shape_layout(const p2v_shape *shape, p2v_layout *out);
+int p2v_challenges_words(const p2v_shape *shape);
+/* `FromJSON VerifierOnlyCircuitData`: out[vkey_words] = cap ++ circuit_digest. */
+int p2v_parse_vkey(const char *json, size_t len, const p2v_shape *shape, uint64_t *out);
+/* `FromJSON ProofWithPublicInputs`: out[blob_words]; P2V_E_SHAPE when a list length differs
+ * from the circuit's shape (the `error`s of safeZip, buildListOracle and validateMerkleCapLength in the reference). */
+int p2v_parse_proof(const char *json, size_t len, const p2v_shape *shape, uint64_t *out);
+
+/* ---- circuits and batches ------------------------------------------------------ */
+/* VerifierCircuitData (Types.hs: verifier_only + verifier_common) resident on the GPU. */
+int p2v_circuit_create(p2v_ctx *ctx, const p2v_shape *shape, const uint64_t *vkey, p2v_circuit **out);
+void p2v_circuit_destroy(p2v_circuit *c);
+
+/* `proofChallenges`, Challenge/Verifier.hs:58-103 (+ `friChallenges`, Challenge/FRI.hs:65-104).
+ *   blobs: AoS [n][blob_words]; challenges_out: SoA [p2v_challenges_words][n]. */
+int p2v_challenges(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n,
+                   uint64_t *challenges_out);
+/* `evalCombinedPlonkConstraints` (Plonk/Vanishing.hs:48-51) + `checkCombinedPlonkEquations'`
+ * (Plonk/Verifier.hs:35-52).  combined_out: SoA [num_challenges*2][n] (may be NULL);
+ * eq_ok_mask: [n] bytes, bit i = round i holds (may be NULL). */
+int p2v_constraints(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n,
+                    uint64_t *combined_out, uint8_t *eq_ok_mask);
+/* `checkFRIProof`, Plonk/FRI.hs:358-407.  status [n] uses the P2V_ST_* encoding restricted to the
+ * FRI codes; query_status (optional) [n][num_queries] per-query codes; debug outputs optional:
+ * folded_out SoA [2][n*num_queries] = final folding_upstream_eval of every query. */
+int p2v_fri(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n, uint32_t *status,
+            uint32_t *query_status, uint64_t *folded_out);
+/* `verifyProof`, Plonk/Verifier.hs:56-65, for n proofs.
+ *   accept_bits: ceil(n/32) words; status: [n] (may be NULL). */
+int p2v_verify_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n,
+                     uint32_t *accept_bits, uint32_t *status);
+/* Limit on proofs staged per pass (SoA workspace = chunk * blob_words * 8 bytes); 0 = default. */
+int p2v_ctx_set_chunk(p2v_ctx *ctx, size_t proofs_per_chunk);
+
+/* Synthetic batches (north_star: "synthetic batches built from the bundled JSON proofs"):
+ * replicate `template_blob` n times into blobs_out (device AoS [n][blob_words]) and add
+ * tamper_delta[i] (mod p) to word tamper_word[i] of copy i (tamper_word[i] < 0: untouched). */
+int p2v_synth_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *template_blob, size_t n,
+                    const int32_t *tamper_word, const uint64_t *tamper_delta, uint64_t *blobs_out);
+
+/* ---- measurement helpers ------------------------------------------------------- */
+/* Integer-pipe peak microbenchmark: dependent chains of IMAD.WIDE.U32 (mode 0), IMAD (mode 1),
+ * IADD3 (mode 2), LOP3 (mode 3), IMAD.WIDE+IADD3 interleaved (mode 4).  Returns warp-level
+ * instructions/s * 32 (thread ops per second) in *ops_per_s. */
+int p2v_int_pipe_peak(p2v_ctx *ctx, int mode, double *ops_per_s);
+/* Time of the most recent timed section in ms, by name ("stage","challenges","constraints","fri","verdict"). */
+int p2v_ctx_last_ms(p2v_ctx *ctx, const char *section, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P2V_H */

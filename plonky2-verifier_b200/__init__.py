@@ -1,0 +1,435 @@
+"""plonky2-verifier_b200 — B200-native batch Plonky2 verifier (host-side Python mirror).
+
+The product is `libp2v.so` (hand-written sm_100a CUDA + C++ host code behind the C ABI in
+`include/p2v.h`).  This module is the thin ctypes layer over it, named after the reference's
+module surface so parity tests read like the reference:
+
+    permutation / sponge / compress / checkMerkleProof     src/Hash/*.hs
+    proofChallenges                                         src/Challenge/Verifier.hs:58
+    evalCombinedPlonkConstraints / checkCombinedPlonkEquations   src/Plonk/Vanishing.hs:48, Plonk/Verifier.hs:31
+    checkFRIProof                                           src/Plonk/FRI.hs:358
+    verifyProof                                             src/Plonk/Verifier.hs:56
+
+There is NO CPU fallback: if the CUDA library is missing or no sm_100 GPU is present, calls raise.
+Arrays are numpy (host) or anything exposing `data_ptr()` (torch CUDA tensors = device pointers).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libp2v.so")
+
+P2V_MAX_GATES = 32
+P2V_MAX_GROUPS = 8
+P2V_MAX_ROUTED = 128
+P2V_MAX_STEPS = 8
+P2V_MAX_LUTS = 8
+P2V_MAX_WEIGHTS = 64
+
+GATE_KINDS = [
+    "ArithmeticGate", "ArithmeticExtensionGate", "BaseSumGate", "CosetInterpolationGate", "ConstantGate",
+    "ExponentiationGate", "LookupGate", "LookupTableGate", "MulExtensionGate", "NoopGate", "PublicInputGate",
+    "PoseidonGate", "PoseidonMdsGate", "RandomAccessGate", "ReducingGate", "ReducingExtensionGate", "UnknownGate",
+]
+
+ST_ACCEPT, ST_FALSE_EQS, ST_FALSE_POW, ST_FALSE_FINAL = 0, 1, 2, 3
+ST_ERR_INIT_MERKLE, ST_ERR_STEP_MERKLE, ST_ERR_STEP_EVAL = 16, 17, 18
+
+
+class P2VError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libp2v error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Gate(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("kind", "p0", "p1", "p2", "group", "num_constraints", "weights_off", "weights_len")]
+
+
+class Shape(C.Structure):
+    _fields_ = [
+        ("num_wires", C.c_int32), ("num_routed_wires", C.c_int32), ("num_gate_constants", C.c_int32),
+        ("num_challenges", C.c_int32),
+        ("degree_bits", C.c_int32), ("rate_bits", C.c_int32), ("cap_height", C.c_int32), ("pow_bits", C.c_int32),
+        ("num_queries", C.c_int32), ("num_steps", C.c_int32), ("step_arity_bits", C.c_int32 * P2V_MAX_STEPS),
+        ("final_poly_len", C.c_int32),
+        ("quotient_degree_factor", C.c_int32), ("num_constants", C.c_int32), ("num_public_inputs", C.c_int32),
+        ("num_partial_products", C.c_int32), ("num_lookup_polys", C.c_int32), ("num_lookup_selectors", C.c_int32),
+        ("num_gates", C.c_int32), ("num_groups", C.c_int32),
+        ("group_start", C.c_int32 * P2V_MAX_GROUPS), ("group_end", C.c_int32 * P2V_MAX_GROUPS),
+        ("gates", Gate * P2V_MAX_GATES),
+        ("num_weights", C.c_int32), ("weights", C.c_uint64 * P2V_MAX_WEIGHTS),
+        ("k_is", C.c_uint64 * P2V_MAX_ROUTED),
+        ("num_luts", C.c_int32), ("lut_off", C.c_int32 * (P2V_MAX_LUTS + 1)),
+        ("lut_pairs", C.POINTER(C.c_uint64)),
+    ]
+
+
+class Layout(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "cap_words", "off_wires_cap", "off_zs_pp_cap", "off_quotient_cap",
+        "off_open_constants", "off_open_sigmas", "off_open_wires", "off_open_zs", "off_open_zs_next",
+        "off_open_pp", "off_open_quotient", "off_open_lookup_zs", "off_open_lookup_zs_next",
+        "n_open_constants", "n_open_sigmas", "n_open_wires", "n_open_zs", "n_open_zs_next",
+        "n_open_pp", "n_open_quotient", "n_open_lookup_zs", "n_open_lookup_zs_next",
+        "off_commit_caps", "off_final_poly", "off_pow_witness", "off_public_inputs", "proof_words")] + [
+        ("oracle_width", C.c_int32 * 4), ("init_path_len", C.c_int32),
+        ("q_off_leaf", C.c_int32 * 4), ("q_off_sibs", C.c_int32 * 4),
+        ("q_off_step_evals", C.c_int32 * P2V_MAX_STEPS), ("q_off_step_sibs", C.c_int32 * P2V_MAX_STEPS),
+        ("step_path_len", C.c_int32 * P2V_MAX_STEPS),
+        ("query_words", C.c_int32), ("blob_words", C.c_int32), ("vkey_words", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def build(force=False, verbose=False):
+    """Compile libp2v.so in-tree (nvcc, sm_100a)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_p2v_build", os.path.join(_HERE, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build(force=force, verbose=verbose)
+
+
+def lib():
+    """The loaded C-ABI library.  Fails loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise P2VError(-3, "libp2v.so is not built (run `python plonky2-verifier_b200/build.py`); "
+                           "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, u64p, u32p, u8p, sz = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t
+    sig = {
+        "p2v_abi_version": (C.c_int, []),
+        "p2v_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "p2v_ctx_destroy": (None, [vp]),
+        "p2v_last_error": (C.c_char_p, [vp]),
+        "p2v_ctx_stream": (vp, [vp]),
+        "p2v_ctx_sync": (C.c_int, [vp]),
+        "p2v_ctx_launch_count": (C.c_uint64, [vp]),
+        "p2v_host_alloc": (C.c_int, [sz, C.POINTER(vp)]),
+        "p2v_host_free": (None, [vp]),
+        "p2v_poseidon_permute": (C.c_int, [vp, u64p, u64p, sz]),
+        "p2v_hash_leaves": (C.c_int, [vp, u64p, C.c_uint32, sz, u64p]),
+        "p2v_compress": (C.c_int, [vp, u64p, u64p, u64p, sz]),
+        "p2v_merkle_verify": (C.c_int, [vp, u64p, C.c_uint32, u32p, u64p, C.c_uint32, u64p, C.c_uint32, sz, u32p, u64p]),
+        "p2v_merkle_build": (C.c_int, [vp, u64p, C.c_uint32, C.c_uint32, C.c_uint32, u64p]),
+        "p2v_merkle_open": (C.c_int, [vp, u64p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p, sz, u64p, u64p, u64p]),
+        "p2v_parse_common": (C.c_int, [C.c_char_p, sz, C.POINTER(Shape)]),
+        "p2v_shape_free": (None, [C.POINTER(Shape)]),
+        "p2v_parse_gate": (C.c_int, [C.c_char_p, sz, C.POINTER(Gate), u64p]),
+        "p2v_shape_layout": (C.c_int, [C.POINTER(Shape), C.POINTER(Layout)]),
+        "p2v_challenges_words": (C.c_int, [C.POINTER(Shape)]),
+        "p2v_parse_vkey": (C.c_int, [C.c_char_p, sz, C.POINTER(Shape), u64p]),
+        "p2v_parse_proof": (C.c_int, [C.c_char_p, sz, C.POINTER(Shape), u64p]),
+        "p2v_circuit_create": (C.c_int, [vp, C.POINTER(Shape), u64p, C.POINTER(vp)]),
+        "p2v_circuit_destroy": (None, [vp]),
+        "p2v_challenges": (C.c_int, [vp, vp, u64p, sz, u64p]),
+        "p2v_constraints": (C.c_int, [vp, vp, u64p, sz, u64p, u8p]),
+        "p2v_fri": (C.c_int, [vp, vp, u64p, sz, u32p, u32p, u64p]),
+        "p2v_verify_batch": (C.c_int, [vp, vp, u64p, sz, u32p, u32p]),
+        "p2v_ctx_set_chunk": (C.c_int, [vp, sz]),
+        "p2v_synth_batch": (C.c_int, [vp, vp, u64p, sz, C.c_void_p, u64p, u64p]),
+        "p2v_int_pipe_peak": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double)]),
+        "p2v_ctx_last_ms": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_float)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError if include/p2v.h and the library ever diverge
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "p2v_abi_version", "p2v_ctx_create", "p2v_ctx_destroy", "p2v_last_error", "p2v_ctx_stream", "p2v_ctx_sync",
+    "p2v_ctx_launch_count", "p2v_host_alloc", "p2v_host_free", "p2v_poseidon_permute", "p2v_hash_leaves",
+    "p2v_compress", "p2v_merkle_verify", "p2v_merkle_build", "p2v_merkle_open", "p2v_parse_common",
+    "p2v_shape_free", "p2v_parse_gate", "p2v_shape_layout", "p2v_challenges_words", "p2v_parse_vkey",
+    "p2v_parse_proof", "p2v_circuit_create", "p2v_circuit_destroy", "p2v_challenges", "p2v_constraints",
+    "p2v_fri", "p2v_verify_batch", "p2v_ctx_set_chunk", "p2v_synth_batch", "p2v_int_pipe_peak", "p2v_ctx_last_ms",
+]
+
+
+def _ptr(a):
+    """Raw address of a numpy array (host) or a torch tensor (host or device); None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        if not a.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return a.data_ptr()
+    if isinstance(a, int):
+        return a
+    raise TypeError("expected numpy array, torch tensor or raw address, got %r" % type(a))
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+# ---- host-only parsers (work without a GPU) --------------------------------------------------
+
+def parse_common(json_text):
+    """`FromJSON CommonCircuitData` (Types.hs:70) -> Shape."""
+    if isinstance(json_text, str):
+        json_text = json_text.encode()
+    sh = Shape()
+    rc = lib().p2v_parse_common(json_text, len(json_text), C.byref(sh))
+    if rc:
+        raise P2VError(rc, lib().p2v_last_error(None).decode())
+    return sh
+
+
+def parse_gate(s):
+    """`recognizeGate` (Gate/Parser.hs:107) -> (Gate, weights list)."""
+    if isinstance(s, str):
+        s = s.encode()
+    g = Gate()
+    w = np.zeros(P2V_MAX_WEIGHTS, dtype=np.uint64)
+    rc = lib().p2v_parse_gate(s, len(s), C.byref(g), w.ctypes.data)
+    if rc:
+        raise P2VError(rc, lib().p2v_last_error(None).decode())
+    return g, [int(x) for x in w[: g.weights_len]]
+
+
+def shape_layout(shape):
+    lay = Layout()
+    rc = lib().p2v_shape_layout(C.byref(shape), C.byref(lay))
+    if rc:
+        raise P2VError(rc, lib().p2v_last_error(None).decode())
+    return lay
+
+
+def challenges_words(shape):
+    return lib().p2v_challenges_words(C.byref(shape))
+
+
+def parse_vkey(json_text, shape):
+    if isinstance(json_text, str):
+        json_text = json_text.encode()
+    lay = shape_layout(shape)
+    out = np.zeros(lay.vkey_words, dtype=np.uint64)
+    rc = lib().p2v_parse_vkey(json_text, len(json_text), C.byref(shape), out.ctypes.data)
+    if rc:
+        raise P2VError(rc, lib().p2v_last_error(None).decode())
+    return out
+
+
+def parse_proof(json_text, shape):
+    if isinstance(json_text, str):
+        json_text = json_text.encode()
+    lay = shape_layout(shape)
+    out = np.zeros(lay.blob_words, dtype=np.uint64)
+    rc = lib().p2v_parse_proof(json_text, len(json_text), C.byref(shape), out.ctypes.data)
+    if rc:
+        raise P2VError(rc, lib().p2v_last_error(None).decode())
+    return out
+
+
+# ---- GPU context -------------------------------------------------------------------------------
+
+class Context:
+    """One GPU, one stream.  All methods run on the GPU through the C ABI."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().p2v_ctx_create(int(device), C.byref(self._h))
+        if rc:
+            raise P2VError(rc, lib().p2v_last_error(None).decode())
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().p2v_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise P2VError(rc, lib().p2v_last_error(self._h).decode())
+
+    @property
+    def stream(self):
+        return lib().p2v_ctx_stream(self._h)
+
+    def sync(self):
+        self._check(lib().p2v_ctx_sync(self._h))
+
+    @property
+    def launch_count(self):
+        return int(lib().p2v_ctx_launch_count(self._h))
+
+    def set_chunk(self, n):
+        self._check(lib().p2v_ctx_set_chunk(self._h, int(n)))
+
+    def last_ms(self, section):
+        v = C.c_float()
+        self._check(lib().p2v_ctx_last_ms(self._h, section.encode(), C.byref(v)))
+        return v.value
+
+    def int_pipe_peak(self, mode=0):
+        v = C.c_double()
+        self._check(lib().p2v_int_pipe_peak(self._h, int(mode), C.byref(v)))
+        return v.value
+
+    # -- L2 Hash (names follow src/Hash/*.hs) --
+    def permutation(self, states, out=None):
+        """states: SoA [12][n] u64.  `permutation`, Hash/Poseidon.hs:42."""
+        n = states.shape[1]
+        if out is None:
+            out = np.empty((12, n), dtype=np.uint64)
+        self._check(lib().p2v_poseidon_permute(self._h, _ptr(states), _ptr(out), n))
+        return out
+
+    def sponge(self, leaves, out=None):
+        """leaves: SoA [w][n].  `sponge`, Hash/Sponge.hs:26 -> digests SoA [4][n]."""
+        w, n = leaves.shape
+        if out is None:
+            out = np.empty((4, n), dtype=np.uint64)
+        self._check(lib().p2v_hash_leaves(self._h, _ptr(leaves) if w else None, w, n, _ptr(out)))
+        return out
+
+    def compress(self, left, right, out=None):
+        n = left.shape[1]
+        if out is None:
+            out = np.empty((4, n), dtype=np.uint64)
+        self._check(lib().p2v_compress(self._h, _ptr(left), _ptr(right), _ptr(out), n))
+        return out
+
+    def checkMerkleProof(self, cap, idx, leaves, siblings, want_roots=False, ok_bits=None, roots=None):
+        """`checkMerkleProof`, Hash/Merkle.hs:39, n openings against one cap.
+        cap [2^h][4]; idx [n] u32; leaves SoA [w][n]; siblings SoA [len*4][n] -> (ok bool[n], roots?)"""
+        w, n = leaves.shape
+        path_len = siblings.shape[0] // 4
+        cap_height = int(cap.shape[0]).bit_length() - 1
+        host_bits = ok_bits is None
+        if ok_bits is None:
+            ok_bits = np.zeros((n + 31) // 32, dtype=np.uint32)
+        if want_roots and roots is None:
+            roots = np.empty((4, n), dtype=np.uint64)
+        self._check(lib().p2v_merkle_verify(self._h, _ptr(leaves) if w else None, w, _ptr(idx),
+                                            _ptr(siblings) if path_len else None, path_len, _ptr(cap), cap_height,
+                                            n, _ptr(ok_bits), _ptr(roots)))
+        ok = unpack_bits(ok_bits, n) if host_bits else ok_bits
+        return (ok, roots) if want_roots else ok
+
+    def merkle_build(self, leaves, log_n, cap_height, out=None):
+        w = leaves.shape[0]
+        total = 4 * ((2 << log_n) - (1 << cap_height))
+        if out is None:
+            out = np.empty(total, dtype=np.uint64)
+        self._check(lib().p2v_merkle_build(self._h, _ptr(leaves), w, log_n, cap_height, _ptr(out)))
+        return out
+
+    def merkle_open(self, leaves, log_n, cap_height, digests, idx, leaves_out=None, sibs_out=None, cap_out=None):
+        w = leaves.shape[0]
+        n = idx.shape[0]
+        if leaves_out is None:
+            leaves_out = np.empty((w, n), dtype=np.uint64)
+            sibs_out = np.empty(((log_n - cap_height) * 4, n), dtype=np.uint64)
+            cap_out = np.empty((1 << cap_height, 4), dtype=np.uint64)
+        self._check(lib().p2v_merkle_open(self._h, _ptr(leaves), w, log_n, cap_height, _ptr(digests), _ptr(idx), n,
+                                          _ptr(leaves_out), _ptr(sibs_out), _ptr(cap_out)))
+        return leaves_out, sibs_out, cap_out
+
+
+def unpack_bits(words, n):
+    """ceil(n/32) u32 words -> bool[n] (bit i%32 of word i/32)."""
+    w = np.asarray(words, dtype=np.uint32)
+    bits = ((w[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(bool).reshape(-1)
+    return bits[:n]
+
+
+class Circuit:
+    """`VerifierCircuitData` (common + verifier-only data) resident on a Context's GPU."""
+
+    def __init__(self, ctx, shape, vkey):
+        self.ctx = ctx
+        self.shape = shape
+        self.layout = shape_layout(shape)
+        self.vkey = _u64(vkey)
+        if self.vkey.size != self.layout.vkey_words:
+            raise ValueError("vkey has %d words, shape expects %d" % (self.vkey.size, self.layout.vkey_words))
+        self._h = C.c_void_p()
+        ctx._check(lib().p2v_circuit_create(ctx._h, C.byref(shape), _ptr(self.vkey), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().p2v_circuit_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _n(self, blobs, n):
+        if n is not None:
+            return int(n)
+        return int(blobs.shape[0]) if getattr(blobs, "ndim", 1) == 2 else int(blobs.size // self.layout.blob_words)
+
+    def proofChallenges(self, blobs, n=None, out=None):
+        """`proofChallenges`, Challenge/Verifier.hs:58.  blobs AoS [n][blob_words] -> SoA [words][n]."""
+        n = self._n(blobs, n)
+        cw = challenges_words(self.shape)
+        if out is None:
+            out = np.empty((cw, n), dtype=np.uint64)
+        self.ctx._check(lib().p2v_challenges(self.ctx._h, self._h, _ptr(blobs), n, _ptr(out)))
+        return out
+
+    def evalCombinedPlonkConstraints(self, blobs, n=None):
+        """Plonk/Vanishing.hs:48 + Plonk/Verifier.hs:35 -> (combined SoA [2r][n], eq_ok_mask u8[n])."""
+        n = self._n(blobs, n)
+        r = self.shape.num_challenges
+        comb = np.empty((2 * r, n), dtype=np.uint64)
+        mask = np.empty(n, dtype=np.uint8)
+        self.ctx._check(lib().p2v_constraints(self.ctx._h, self._h, _ptr(blobs), n, _ptr(comb), _ptr(mask)))
+        return comb, mask
+
+    def checkFRIProof(self, blobs, n=None, want_debug=False):
+        """`checkFRIProof`, Plonk/FRI.hs:358 -> status u32[n] (+ per-query status, folded evals)."""
+        n = self._n(blobs, n)
+        q = self.shape.num_queries
+        status = np.empty(n, dtype=np.uint32)
+        qs = np.empty((n, q), dtype=np.uint32) if want_debug else None
+        folded = np.empty((2, n * q), dtype=np.uint64) if want_debug else None
+        self.ctx._check(lib().p2v_fri(self.ctx._h, self._h, _ptr(blobs), n, _ptr(status), _ptr(qs), _ptr(folded)))
+        return (status, qs, folded) if want_debug else status
+
+    def verifyProof(self, blobs, n=None, accept_bits=None, status=None):
+        """`verifyProof`, Plonk/Verifier.hs:56, for a batch -> (accept bool[n], status u32[n])."""
+        n = self._n(blobs, n)
+        host = accept_bits is None
+        if accept_bits is None:
+            accept_bits = np.zeros((n + 31) // 32, dtype=np.uint32)
+        if status is None:
+            status = np.empty(n, dtype=np.uint32)
+        self.ctx._check(lib().p2v_verify_batch(self.ctx._h, self._h, _ptr(blobs), n, _ptr(accept_bits), _ptr(status)))
+        return (unpack_bits(accept_bits, n), status) if host else (accept_bits, status)
+
+    def synth_batch(self, template_blob, n, tamper_word, tamper_delta, blobs_out):
+        """Replicate + tamper a template into a device AoS batch (synthetic inputs)."""
+        tw = np.ascontiguousarray(tamper_word, dtype=np.int32)
+        td = _u64(tamper_delta)
+        self.ctx._check(lib().p2v_synth_batch(self.ctx._h, self._h, _ptr(_u64(template_blob)), int(n), _ptr(tw),
+                                              _ptr(td), _ptr(blobs_out)))
+        return blobs_out

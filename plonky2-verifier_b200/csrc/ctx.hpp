@@ -1,0 +1,110 @@
+// Context, error plumbing and host/device pointer staging shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <map>
+#include <vector>
+#include "../../include/p2v.h"
+
+struct p2v_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  size_t chunk = 0;  // proofs per pass; 0 = default
+  std::map<std::string, float> last_ms;
+  // verify workspace (lazily grown)
+  void *ws = nullptr;
+  size_t ws_bytes = 0;
+  void *stage_buf[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  cudaEvent_t ev[8] = {};
+  cudaEvent_t copy_done[2] = {}, compute_done[2] = {};
+};
+
+extern thread_local std::string p2v_tls_error;
+
+static inline int p2v_fail(p2v_ctx *ctx, int code, const std::string &msg) {
+  p2v_tls_error = msg;
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define P2V_CUDA(ctx, call)                                                                     \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return p2v_fail((ctx), P2V_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+#define P2V_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+  do {                                                                          \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);            \
+    (ctx)->launches++;                                                          \
+    P2V_CUDA((ctx), cudaGetLastError());                                        \
+  } while (0)
+
+static inline bool p2v_is_device_ptr(const void *p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Input that may live on the host: staged to the device through the context's stream.
+struct DevIn {
+  p2v_ctx *ctx;
+  const void *dev = nullptr;
+  void *tmp = nullptr;
+  int init(p2v_ctx *c, const void *p, size_t bytes) {
+    ctx = c;
+    if (!p || bytes == 0) { dev = p; return 0; }
+    if (p2v_is_device_ptr(p)) { dev = p; return 0; }
+    P2V_CUDA(ctx, cudaMallocAsync(&tmp, bytes, ctx->stream));
+    P2V_CUDA(ctx, cudaMemcpyAsync(tmp, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    dev = tmp;
+    return 0;
+  }
+  ~DevIn() { if (tmp) cudaFreeAsync(tmp, ctx->stream); }
+  template <class T> const T *as() const { return (const T *)dev; }
+};
+
+// Output that may live on the host: computed on the device, copied back by finish().
+struct DevOut {
+  p2v_ctx *ctx;
+  void *host = nullptr;
+  void *dev = nullptr;
+  void *tmp = nullptr;
+  size_t bytes = 0;
+  int init(p2v_ctx *c, void *p, size_t nbytes) {
+    ctx = c;
+    bytes = nbytes;
+    if (!p || nbytes == 0) { dev = nullptr; return 0; }
+    if (p2v_is_device_ptr(p)) { dev = p; return 0; }
+    host = p;
+    P2V_CUDA(ctx, cudaMallocAsync(&tmp, nbytes, ctx->stream));
+    dev = tmp;
+    return 0;
+  }
+  // enqueue the copy back; the caller synchronises the stream afterwards
+  int finish() {
+    if (tmp && host) P2V_CUDA(ctx, cudaMemcpyAsync(host, tmp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+  }
+  ~DevOut() { if (tmp) cudaFreeAsync(tmp, ctx->stream); }
+  template <class T> T *as() const { return (T *)dev; }
+};
+
+static inline int p2v_grid_for(p2v_ctx *ctx, size_t n, int block, int blocks_per_sm) {
+  size_t need = (n + block - 1) / block;
+  size_t cap = (size_t)ctx->sm_count * blocks_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}

@@ -1,0 +1,263 @@
+// C-ABI entry points: context + L2 hash layer (K1-K3) + measurement helpers.  See include/p2v.h.
+#include "ctx.hpp"
+#include "hash_kernels.cuh"
+
+thread_local std::string p2v_tls_error;
+
+extern "C" {
+
+int p2v_abi_version(void) { return P2V_ABI_VERSION; }
+
+const char *p2v_last_error(const p2v_ctx *ctx) { return ctx ? ctx->err.c_str() : p2v_tls_error.c_str(); }
+
+int p2v_ctx_create(int device, p2v_ctx **out) {
+  if (!out) return p2v_fail(nullptr, P2V_E_INVALID, "p2v_ctx_create: out is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return p2v_fail(nullptr, P2V_E_NOGPU,
+                    "p2v_ctx_create: no CUDA device available; libp2v has no CPU fallback");
+  }
+  if (device < 0 || device >= count) return p2v_fail(nullptr, P2V_E_INVALID, "p2v_ctx_create: bad device index");
+  cudaDeviceProp prop;
+  P2V_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return p2v_fail(nullptr, P2V_E_NOGPU, "p2v_ctx_create: kernels are built for sm_100a only (Blackwell B200)");
+  P2V_CUDA(nullptr, cudaSetDevice(device));
+  p2v_ctx *ctx = new p2v_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (auto &ev : ctx->ev) P2V_CUDA(nullptr, cudaEventCreate(&ev));
+  for (int i = 0; i < 2; i++) {
+    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming));
+    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->compute_done[i], cudaEventDisableTiming));
+  }
+  *out = ctx;
+  return P2V_OK;
+}
+
+void p2v_ctx_destroy(p2v_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->ws) cudaFree(ctx->ws);
+  for (auto &b : ctx->stage_buf)
+    if (b) cudaFree(b);
+  for (auto &ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (int i = 0; i < 2; i++) {
+    if (ctx->copy_done[i]) cudaEventDestroy(ctx->copy_done[i]);
+    if (ctx->compute_done[i]) cudaEventDestroy(ctx->compute_done[i]);
+  }
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+void *p2v_ctx_stream(p2v_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int p2v_ctx_sync(p2v_ctx *ctx) {
+  if (!ctx) return P2V_E_INVALID;
+  P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return P2V_OK;
+}
+
+uint64_t p2v_ctx_launch_count(const p2v_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int p2v_ctx_set_chunk(p2v_ctx *ctx, size_t proofs_per_chunk) {
+  if (!ctx) return P2V_E_INVALID;
+  ctx->chunk = proofs_per_chunk;
+  return P2V_OK;
+}
+
+int p2v_ctx_last_ms(p2v_ctx *ctx, const char *section, float *ms) {
+  if (!ctx || !section || !ms) return P2V_E_INVALID;
+  auto it = ctx->last_ms.find(section);
+  if (it == ctx->last_ms.end()) return p2v_fail(ctx, P2V_E_INVALID, std::string("no timing for section ") + section);
+  *ms = it->second;
+  return P2V_OK;
+}
+
+int p2v_host_alloc(size_t bytes, void **out) {
+  if (!out) return P2V_E_INVALID;
+  cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return p2v_fail(nullptr, P2V_E_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  }
+  return P2V_OK;
+}
+void p2v_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ---- K1 -----------------------------------------------------------------------------------
+int p2v_poseidon_permute(p2v_ctx *ctx, const uint64_t *in, uint64_t *out, size_t n) {
+  if (!ctx || !in || !out) return p2v_fail(ctx, P2V_E_INVALID, "p2v_poseidon_permute: NULL argument");
+  if (n == 0) return P2V_OK;
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevIn din;
+  DevOut dout;
+  int rc;
+  if ((rc = din.init(ctx, in, n * 12 * sizeof(u64)))) return rc;
+  if ((rc = dout.init(ctx, out, n * 12 * sizeof(u64)))) return rc;
+  P2V_LAUNCH(ctx, k_poseidon_permute, p2v_grid_for(ctx, n, 256, 16), 256, 0, din.as<u64>(), dout.as<u64>(), n);
+  if ((rc = dout.finish())) return rc;
+  if (dout.host) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return P2V_OK;
+}
+
+// ---- K2 -----------------------------------------------------------------------------------
+int p2v_hash_leaves(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, size_t n, uint64_t *digests) {
+  if (!ctx || !digests || (!leaves && w)) return p2v_fail(ctx, P2V_E_INVALID, "p2v_hash_leaves: NULL argument");
+  if (n == 0) return P2V_OK;
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevIn din;
+  DevOut dout;
+  int rc;
+  if ((rc = din.init(ctx, leaves, n * (size_t)w * sizeof(u64)))) return rc;
+  if ((rc = dout.init(ctx, digests, n * 4 * sizeof(u64)))) return rc;
+  P2V_LAUNCH(ctx, k_hash_leaves, p2v_grid_for(ctx, n, 256, 16), 256, 0, din.as<u64>(), w, n, dout.as<u64>());
+  if ((rc = dout.finish())) return rc;
+  if (dout.host) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return P2V_OK;
+}
+
+int p2v_compress(p2v_ctx *ctx, const uint64_t *left, const uint64_t *right, uint64_t *out, size_t n) {
+  if (!ctx || !left || !right || !out) return p2v_fail(ctx, P2V_E_INVALID, "p2v_compress: NULL argument");
+  if (n == 0) return P2V_OK;
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevIn dl, dr;
+  DevOut dout;
+  int rc;
+  if ((rc = dl.init(ctx, left, n * 4 * sizeof(u64)))) return rc;
+  if ((rc = dr.init(ctx, right, n * 4 * sizeof(u64)))) return rc;
+  if ((rc = dout.init(ctx, out, n * 4 * sizeof(u64)))) return rc;
+  P2V_LAUNCH(ctx, k_compress, p2v_grid_for(ctx, n, 256, 16), 256, 0, dl.as<u64>(), dr.as<u64>(), n, (size_t)1,
+             dout.as<u64>(), n, n);
+  if ((rc = dout.finish())) return rc;
+  if (dout.host) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return P2V_OK;
+}
+
+// ---- K3 -----------------------------------------------------------------------------------
+int p2v_merkle_verify(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, const uint32_t *idx, const uint64_t *siblings,
+                      uint32_t path_len, const uint64_t *cap, uint32_t cap_height, size_t n, uint32_t *ok_bits,
+                      uint64_t *roots_out) {
+  if (!ctx || !idx || !cap || !ok_bits || (!leaves && w) || (!siblings && path_len))
+    return p2v_fail(ctx, P2V_E_INVALID, "p2v_merkle_verify: NULL argument");
+  if (cap_height > 20 || path_len > 32) return p2v_fail(ctx, P2V_E_INVALID, "p2v_merkle_verify: bad heights");
+  if (n == 0) return P2V_OK;
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevIn dl, di, ds, dc;
+  DevOut dok, droots;
+  int rc;
+  if ((rc = dl.init(ctx, leaves, n * (size_t)w * sizeof(u64)))) return rc;
+  if ((rc = di.init(ctx, idx, n * sizeof(u32)))) return rc;
+  if ((rc = ds.init(ctx, siblings, n * (size_t)path_len * 4 * sizeof(u64)))) return rc;
+  if ((rc = dc.init(ctx, cap, ((size_t)4 << cap_height) * sizeof(u64)))) return rc;
+  if ((rc = dok.init(ctx, ok_bits, (n + 31) / 32 * sizeof(u32)))) return rc;
+  if ((rc = droots.init(ctx, roots_out, n * 4 * sizeof(u64)))) return rc;
+  P2V_LAUNCH(ctx, k_merkle_verify, p2v_grid_for(ctx, n, 256, 16), 256, 0, dl.as<u64>(), w, di.as<u32>(), ds.as<u64>(),
+             path_len, dc.as<u64>(), cap_height, n, dok.as<u32>(), droots.as<u64>());
+  if ((rc = dok.finish())) return rc;
+  if ((rc = droots.finish())) return rc;
+  if (dok.host || droots.host) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return P2V_OK;
+}
+
+int p2v_merkle_build(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, uint32_t log_n, uint32_t cap_height,
+                     uint64_t *digests_out) {
+  if (!ctx || !digests_out || (!leaves && w)) return p2v_fail(ctx, P2V_E_INVALID, "p2v_merkle_build: NULL argument");
+  if (log_n > 30 || cap_height > log_n) return p2v_fail(ctx, P2V_E_INVALID, "p2v_merkle_build: bad heights");
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t n = (size_t)1 << log_n;
+  size_t total = 4 * (((size_t)2 << log_n) - ((size_t)1 << cap_height));
+  DevIn dl;
+  DevOut dout;
+  int rc;
+  if ((rc = dl.init(ctx, leaves, n * (size_t)w * sizeof(u64)))) return rc;
+  if ((rc = dout.init(ctx, digests_out, total * sizeof(u64)))) return rc;
+  u64 *lvl = dout.as<u64>();
+  P2V_LAUNCH(ctx, k_hash_leaves, p2v_grid_for(ctx, n, 256, 16), 256, 0, dl.as<u64>(), w, n, lvl);
+  for (uint32_t l = 0; l < log_n - cap_height; l++) {
+    size_t cur_n = n >> l, nxt_n = cur_n >> 1;
+    u64 *nxt = lvl + 4 * cur_n;
+    // children 2t (left) and 2t+1 (right) of level l -> node t of level l+1
+    P2V_LAUNCH(ctx, k_compress, p2v_grid_for(ctx, nxt_n, 256, 16), 256, 0, lvl, lvl + 1, cur_n, (size_t)2, nxt, nxt_n,
+               nxt_n);
+    lvl = nxt;
+  }
+  if ((rc = dout.finish())) return rc;
+  if (dout.host) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return P2V_OK;
+}
+
+int p2v_merkle_open(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, uint32_t log_n, uint32_t cap_height,
+                    const uint64_t *digests, const uint32_t *idx, size_t n, uint64_t *leaves_out,
+                    uint64_t *siblings_out, uint64_t *cap_out) {
+  if (!ctx || !digests || !idx || !leaves_out || !siblings_out || !cap_out || (!leaves && w))
+    return p2v_fail(ctx, P2V_E_INVALID, "p2v_merkle_open: NULL argument");
+  if (log_n > 30 || cap_height > log_n) return p2v_fail(ctx, P2V_E_INVALID, "p2v_merkle_open: bad heights");
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t n_leaves = (size_t)1 << log_n;
+  size_t total = 4 * (((size_t)2 << log_n) - ((size_t)1 << cap_height));
+  uint32_t path_len = log_n - cap_height;
+  DevIn dl, dd, di;
+  DevOut dlo, dso, dco;
+  int rc;
+  if ((rc = dl.init(ctx, leaves, n_leaves * (size_t)w * sizeof(u64)))) return rc;
+  if ((rc = dd.init(ctx, digests, total * sizeof(u64)))) return rc;
+  if ((rc = di.init(ctx, idx, n * sizeof(u32)))) return rc;
+  if ((rc = dlo.init(ctx, leaves_out, n * (size_t)w * sizeof(u64)))) return rc;
+  if ((rc = dso.init(ctx, siblings_out, n * (size_t)path_len * 4 * sizeof(u64)))) return rc;
+  if ((rc = dco.init(ctx, cap_out, ((size_t)4 << cap_height) * sizeof(u64)))) return rc;
+  if (n) {
+    P2V_LAUNCH(ctx, k_merkle_open, p2v_grid_for(ctx, n, 256, 16), 256, 0, dl.as<u64>(), w, log_n, cap_height,
+               dd.as<u64>(), di.as<u32>(), n, dlo.as<u64>(), dso.as<u64>());
+  }
+  uint32_t ncap = 1u << cap_height;
+  const u64 *cap_level = dd.as<u64>() + (total - 4 * (size_t)ncap);
+  P2V_LAUNCH(ctx, k_cap_transpose, (ncap * 4 + 255) / 256, 256, 0, cap_level, ncap, dco.as<u64>());
+  if ((rc = dlo.finish())) return rc;
+  if ((rc = dso.finish())) return rc;
+  if ((rc = dco.finish())) return rc;
+  if (dlo.host || dso.host || dco.host) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return P2V_OK;
+}
+
+// ---- measurement helper -------------------------------------------------------------------
+int p2v_int_pipe_peak(p2v_ctx *ctx, int mode, double *ops_per_s) {
+  if (!ctx || !ops_per_s || mode < 0 || mode > 4) return p2v_fail(ctx, P2V_E_INVALID, "p2v_int_pipe_peak: bad argument");
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  u64 *d = nullptr;
+  P2V_CUDA(ctx, cudaMalloc(&d, 8));
+  const uint32_t iters = 4096;
+  int grid = ctx->sm_count * 8, block = 256;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    P2V_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    switch (mode) {
+      case 0: P2V_LAUNCH(ctx, k_int_pipe<0>, grid, block, 0, d, iters, 12345u); break;
+      case 1: P2V_LAUNCH(ctx, k_int_pipe<1>, grid, block, 0, d, iters, 12345u); break;
+      case 2: P2V_LAUNCH(ctx, k_int_pipe<2>, grid, block, 0, d, iters, 12345u); break;
+      case 3: P2V_LAUNCH(ctx, k_int_pipe<3>, grid, block, 0, d, iters, 12345u); break;
+      default: P2V_LAUNCH(ctx, k_int_pipe<4>, grid, block, 0, d, iters, 12345u); break;
+    }
+    P2V_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    P2V_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
+    float ms = 0;
+    P2V_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaFree(d);
+  double per_thread = (double)iters * 64.0 * (mode == 4 ? 2.0 : 1.0);
+  *ops_per_s = per_thread * (double)grid * block / (best * 1e-3);
+  return P2V_OK;
+}
+
+}  // extern "C"

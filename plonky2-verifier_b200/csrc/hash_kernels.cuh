@@ -1,0 +1,187 @@
+// K1-K3: batched Poseidon permutation, leaf sponge, 2-to-1 compression, Merkle path checks and
+// the synthetic-tree builder.  One thread per state / sponge / path; every plane access is
+// [word][item] so a warp reads 256 contiguous bytes per word.
+#pragma once
+#include "poseidon.cuh"
+
+// K1: `permutation`, Hash/Poseidon.hs:42.  in/out SoA [12][n].
+__global__ void __launch_bounds__(256) k_poseidon_permute(const u64 *__restrict__ in, u64 *__restrict__ out, size_t n) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = in[(size_t)i * n + t];
+    poseidon_permute(s);
+#pragma unroll
+    for (int i = 0; i < 12; i++) out[(size_t)i * n + t] = gl_canon(s[i]);
+  }
+}
+
+// Sponge over a strided column of words: word j of item t is at base[j*stride + t].
+// `sponge`, Hash/Sponge.hs:26-31: overwrite mode, rate 8, no padding, w = 0 -> zero digest.
+// Returns the state; digest = s[0..3] (lazy).
+__device__ __forceinline__ void sponge_absorb_strided(u64 (&s)[12], const u64 *__restrict__ base, size_t stride, u32 w) {
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = 0;
+  u32 nblk = (w + 7) / 8;
+#pragma unroll 1
+  for (u32 b = 0; b < nblk; b++) {
+    u32 k = w - b * 8;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if ((u32)i < k) s[i] = base[(size_t)(b * 8 + i) * stride];
+    poseidon_permute(s);
+  }
+}
+
+// K2: leaf hashing.  leaves SoA [w][n] -> digests SoA [4][n]
+__global__ void __launch_bounds__(256) k_hash_leaves(const u64 *__restrict__ leaves, u32 w, size_t n, u64 *__restrict__ digests) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    u64 s[12];
+    sponge_absorb_strided(s, leaves + t, n, w);
+#pragma unroll
+    for (int i = 0; i < 4; i++) digests[(size_t)i * n + t] = gl_canon(s[i]);
+  }
+}
+
+// `compress`, Hash/Merkle.hs:21-23.  out may alias neither input.
+// General strided form used by the tree builder: left word k of item t at left[k*ls + t*lm].
+__global__ void __launch_bounds__(256) k_compress(const u64 *__restrict__ left, const u64 *__restrict__ right, size_t in_stride,
+                                                  size_t in_mul, u64 *__restrict__ out, size_t out_stride, size_t n) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      s[i] = left[(size_t)i * in_stride + t * in_mul];
+      s[4 + i] = right[(size_t)i * in_stride + t * in_mul];
+      s[8 + i] = 0;
+    }
+    poseidon_permute(s);
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[(size_t)i * out_stride + t] = gl_canon(s[i]);
+  }
+}
+
+// K3: `checkMerkleProof cap idx leaf proof`, Hash/Merkle.hs:27-42, one thread per opening.
+// A single permutation call site: iteration 0..nblk-1 absorb the leaf, then one compression per
+// sibling (even idx => node is the left input, Merkle.hs:34-36).
+__global__ void __launch_bounds__(256) k_merkle_verify(const u64 *__restrict__ leaves, u32 w, const u32 *__restrict__ idx,
+                                                       const u64 *__restrict__ siblings, u32 path_len,
+                                                       const u64 *__restrict__ cap, u32 cap_height, size_t n,
+                                                       u32 *__restrict__ ok_bits, u64 *__restrict__ roots_out) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t n_round = (n + 31) / 32 * 32;  // whole warps stay alive for the ballot
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += stride) {
+    bool live = t < n;
+    size_t tt = live ? t : n - 1;
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    u32 nblk = (w + 7) / 8;
+    u32 index = idx[tt];
+    u32 iters = nblk + path_len;
+#pragma unroll 1
+    for (u32 it = 0; it < iters; it++) {
+      if (it < nblk) {
+        u32 k = w - it * 8;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if ((u32)i < k) s[i] = leaves[(size_t)(it * 8 + i) * n + tt];
+      } else {
+        u32 l = it - nblk;
+        u64 sib[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) sib[i] = siblings[(size_t)(l * 4 + i) * n + tt];
+        bool even = (index & 1u) == 0;
+        index >>= 1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          u64 node = s[i];
+          s[i] = even ? node : sib[i];
+          s[4 + i] = even ? sib[i] : node;
+          s[8 + i] = 0;
+        }
+      }
+      poseidon_permute(s);
+    }
+    // w == 0 and path_len == 0: digest is the zero digest (Sponge.hs:28)
+    bool ok = index < (1u << cap_height);
+    u32 ci = ok ? index : 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      u64 v = gl_canon(s[i]);
+      if (roots_out && live) roots_out[(size_t)i * n + t] = v;
+      ok = ok && (v == gl_canon(cap[(size_t)ci * 4 + i]));
+    }
+    u32 ballot = __ballot_sync(0xffffffffu, ok && live);
+    if ((threadIdx.x & 31) == 0) ok_bits[t / 32] = ballot;
+  }
+}
+
+// Gather openings from a built tree (synthetic config 2).
+__global__ void k_merkle_open(const u64 *__restrict__ leaves, u32 w, u32 log_n, u32 cap_height,
+                              const u64 *__restrict__ digests, const u32 *__restrict__ idx, size_t n,
+                              u64 *__restrict__ leaves_out, u64 *__restrict__ siblings_out) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t n_leaves = (size_t)1 << log_n;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    u32 index = idx[t];
+    for (u32 j = 0; j < w; j++) leaves_out[(size_t)j * n + t] = leaves[(size_t)j * n_leaves + index];
+    size_t level_off = 0;  // in digests (4 words each, SoA per level)
+    u32 path_len = log_n - cap_height;
+    for (u32 l = 0; l < path_len; l++) {
+      size_t level_n = n_leaves >> l;
+      u32 sib = (index >> l) ^ 1u;
+      for (int k = 0; k < 4; k++) siblings_out[(size_t)(l * 4 + k) * n + t] = digests[level_off + (size_t)k * level_n + sib];
+      level_off += 4 * level_n;
+    }
+  }
+}
+
+// cap level (SoA [4][2^cap_height]) -> row-major [2^cap_height][4]
+__global__ void k_cap_transpose(const u64 *__restrict__ level, u32 ncap, u64 *__restrict__ cap_out) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ncap * 4) cap_out[(t % ncap) * 4 + t / ncap] = level[t];
+}
+
+// ---- integer-pipe peak microbenchmark (measurement helper) --------------------------------
+// mode 0: IMAD.WIDE.U32 chains, 1: IMAD (32-bit) chains, 2: IADD3 chains, 3: LOP3 chains,
+// mode 4: IMAD.WIDE.U32 and IADD3 interleaved 1:1.  8 independent chains per thread.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_int_pipe(u64 *out, u32 iters, u32 seed) {
+  u32 x = threadIdx.x * 2654435761u + seed;
+  u64 a[8];
+  u32 b[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a[i] = x + i;
+    b[i] = x * (i + 3);
+  }
+#pragma unroll 1
+  for (u32 it = 0; it < iters; it++) {
+#pragma unroll
+    for (int rep = 0; rep < 8; rep++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (MODE == 0) {
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(b[i]), "r"(x));
+        } else if (MODE == 1) {
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(b[i]) : "r"(x), "r"(seed));
+        } else if (MODE == 2) {
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(x));
+        } else if (MODE == 3) {
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[i]) : "r"(x), "r"(seed));
+        } else {
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(b[i]), "r"(x));
+          asm volatile("add.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(seed));
+        }
+      }
+    }
+  }
+  u64 acc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc += a[i] + b[i];
+  if (acc == 0x1234567812345678ULL) out[0] = acc;  // keep the chains alive
+}
