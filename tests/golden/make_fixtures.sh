@@ -1,0 +1,20 @@
+#!/bin/sh
+# Regenerates the bundled JSON fixtures with the trivial-circuit mini-prover (oracle/prover.cpp).
+# The reference bundles none (its json/ directory is git-ignored), so these stand in for
+# "the repo's bundled Plonky2 JSON proof" of BASELINE.json configs[0].  Deterministic (seeded).
+set -e
+cd "$(dirname "$0")/../.."
+make -C oracle -s p2v_prover
+P=oracle/p2v_prover
+G=tests/golden
+$P s12     $G/s12     --seed 1
+$P mid5    $G/mid5    --seed 2
+$P small6  $G/small6  --seed 3
+$P fixed4  $G/fixed4  --seed 4
+$P lookup6 $G/lookup6 --seed 5
+# rejecting proofs that need a prover-side change (re-grinding after the change):
+$P small6 $G/small6_badfinal  --seed 3 --bad-final        # -> FALSE_FINAL
+$P small6 $G/small6_badlayer0 --seed 3 --corrupt-layer 0  # -> ERR_STEP_EVAL(step 0)
+$P small6 $G/small6_badlayer1 --seed 3 --corrupt-layer 1  # -> ERR_STEP_EVAL(step 1)
+# the variants share small6's circuit: keep one copy of common/vkey where identical
+for v in badfinal badlayer0 badlayer1; do rm -f $G/small6_${v}_common.json; done
