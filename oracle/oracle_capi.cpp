@@ -5,7 +5,7 @@
 #include <cstring>
 #include <thread>
 #include <vector>
-#include "hash.hpp"
+#include "plonk.hpp"
 
 using namespace orc;
 
@@ -90,6 +90,94 @@ uint64_t orc_perm_loop(size_t iters, int threads, int which) {
   uint64_t x = 0;
   for (auto v : sums) x ^= v;
   return x;
+}
+
+
+// ---- batch verification (restatement of verifyProof & friends on flat blobs) -----------------
+// shape/vkey/blobs as in include/p2v.h.  Any output pointer may be NULL.
+//   challenges SoA [cw][n]; combined SoA [2r][n]; eqmask [n]; status [n] = verifyProof verdict;
+//   fri_status [n] = checkFRIProof verdict alone; qstatus [n][Q]; folded SoA [2][n*Q] (index p*Q+q).
+// fast != 0 switches the permutation to the bulk form (bit-identical, tests assert it).
+// A C++ exception from the restatement (an `error` site that the fixed shape should make
+// unreachable) is reported as status 0xEE.
+int orc_verify_batch(const p2v_shape *shape, const uint64_t *vkey_words, const uint64_t *blobs, size_t n, int threads, int fast,
+                     uint64_t *challenges, uint64_t *combined, uint8_t *eqmask, uint32_t *status, uint32_t *fri_status,
+                     uint32_t *qstatus, uint64_t *folded, unsigned long long *perm_count) {
+  CommonCircuitData c = commonFromShape(*shape);
+  VerifierOnlyCircuitData vk = vkeyFromWords(c, vkey_words);
+  activePermutation() = fast ? permutationBulk : permutation;
+  size_t bw = 0;
+  {
+    p2v_layout dummy;
+    (void)dummy;
+    ProofWithPublicInputs probe;  // blob size from a round trip of the first proof
+    bw = proofToBlob(proofFromBlob(c, blobs)).size();
+  }
+  if (threads < 1) threads = 1;
+  std::vector<std::thread> th;
+  std::vector<unsigned long long> counts(threads, 0);
+  int Q = c.fri_config.num_query_rounds, r = c.num_challenges;
+  for (int k = 0; k < threads; k++)
+    th.emplace_back([&, k]() {
+      permCounter() = 0;
+      for (size_t p = k; p < n; p += threads) {
+        try {
+          ProofWithPublicInputs pw = proofFromBlob(c, blobs + p * bw);
+          VerifyTrace tr;
+          uint32_t st = verifyProofStatus(c, vk, pw, &tr);
+          if (status) status[p] = st;
+          if (fri_status) fri_status[p] = tr.fri_status;
+          if (challenges) {
+            std::vector<uint64_t> w = challengesToWords(tr.challenges);
+            for (size_t i = 0; i < w.size(); i++) challenges[i * n + p] = w[i];
+          }
+          if (combined)
+            for (int j = 0; j < r; j++) { combined[(2 * j) * n + p] = tr.combined[j].r.v; combined[(2 * j + 1) * n + p] = tr.combined[j].i.v; }
+          if (eqmask) {
+            uint8_t m = 0;
+            for (size_t j = 0; j < tr.eqs_ok.size(); j++) if (tr.eqs_ok[j]) m |= (uint8_t)(1u << j);
+            eqmask[p] = m;
+          }
+          for (int q = 0; q < Q && q < (int)tr.queries.size(); q++) {
+            const QueryTrace &qt = tr.queries[q];
+            if (qstatus) qstatus[p * Q + q] = qt.status == 0 ? 0u : ((uint32_t)qt.status | ((uint32_t)q << 8) | ((uint32_t)qt.detail << 16));
+            if (folded) { folded[p * Q + q] = qt.folded.r.v; folded[n * Q + p * Q + q] = qt.folded.i.v; }
+          }
+        } catch (const std::exception &e) {
+          if (status) status[p] = 0xEE;
+          if (fri_status) fri_status[p] = 0xEE;
+        }
+      }
+      counts[k] = permCounter();
+    });
+  for (auto &t : th) t.join();
+  if (perm_count) { *perm_count = 0; for (auto v : counts) *perm_count += v; }
+  activePermutation() = permutation;
+  return 0;
+}
+
+// unfiltered constraint vector of one gate on given openings (for gate-level differential tests):
+// wires [num_wires][2], consts [num_consts][2], pih[4]; out [max_out][2]; returns the number of constraints
+int orc_gate_constraints(const p2v_shape *shape, int gate_index, const uint64_t *wires, int num_wires, const uint64_t *consts,
+                         int num_consts, const uint64_t *pih, uint64_t *out, int max_out) {
+  CommonCircuitData c = commonFromShape(*shape);
+  EvaluationVars ev;
+  for (int i = 0; i < num_wires; i++) ev.local_wires.push_back(FExt(F(wires[2 * i]), F(wires[2 * i + 1])));
+  for (int i = 0; i < num_consts; i++) ev.local_constants.push_back(FExt(F(consts[2 * i]), F(consts[2 * i + 1])));
+  for (int i = 0; i < 4; i++) ev.public_inputs_hash.push_back(F(pih[i]));
+  try {
+    std::vector<FExt> v = gateConstraints(c.gates.at(gate_index), ev);
+    for (int i = 0; i < (int)v.size() && i < max_out; i++) { out[2 * i] = v[i].r.v; out[2 * i + 1] = v[i].i.v; }
+    return (int)v.size();
+  } catch (const std::exception &e) {
+    return -1;
+  }
+}
+
+// layout implied by a shape, computed by the oracle's own reader/writer (for comparison with p2v_shape_layout)
+size_t orc_blob_words(const p2v_shape *shape, const uint64_t *blob) {
+  CommonCircuitData c = commonFromShape(*shape);
+  return proofToBlob(proofFromBlob(c, blob)).size();
 }
 
 }  // extern "C"

@@ -20,6 +20,7 @@ typedef uint32_t u32;
 
 #define GL_P 0xFFFFFFFF00000001ULL
 #define GL_EPS 0xFFFFFFFFULL /* 2^64 mod p */
+#define GL_MUL_GEN_C 0xc65c18b67785d900ULL /* mulGen, Algebra/Goldilocks.hs:135 */
 
 __device__ __forceinline__ u64 gl_canon(u64 x) { return x >= GL_P ? x - GL_P : x; }
 
@@ -82,12 +83,12 @@ __device__ __forceinline__ u64 gl_pow(u64 x, u64 e) {
   return acc;
 }
 // x^(p-2): inv 0 = 0 exactly like the reference (Algebra/Goldilocks.hs:155-156).
-// Addition chain for p-2 = 2^64 - 2^32 - 1 = (2^32-1)*2^32 + (2^32 - 1): 63 squarings + 9 multiplications... kept simple:
+// Addition chain: 63 squarings + 9 multiplications.
 __device__ __forceinline__ u64 gl_exp_acc(u64 base, u64 tail, int n) {
   for (int i = 0; i < n; i++) base = gl_sqr(base);
   return gl_mul(base, tail);
 }
-__device__ __noinline__ u64 gl_inv(u64 x) {
+static __device__ __noinline__ u64 gl_inv(u64 x) {
   // x^(2^k - 1) ladders
   u64 t2 = gl_exp_acc(x, x, 1);      // x^(2^2-1)
   u64 t3 = gl_exp_acc(t2, x, 1);     // 2^3-1
@@ -97,7 +98,6 @@ __device__ __noinline__ u64 gl_inv(u64 x) {
   u64 t30 = gl_exp_acc(t24, t6, 6);  // 2^30-1
   u64 t31 = gl_exp_acc(t30, x, 1);   // 2^31-1
   u64 t32 = gl_exp_acc(t31, x, 1);   // 2^32-1
-  // p-2 = (2^32-1)*2^32 + (2^32-1) - ... check: p-2 = 2^64-2^32-1 = (2^32-1)*2^32 + (2^32-1) - 2^32 + ... see below
   // p - 2 = 0xFFFFFFFE_FFFFFFFF = (2^31-1)*2^33 + (2^32-1)
   u64 t = t31;
   for (int i = 0; i < 33; i++) t = gl_sqr(t);

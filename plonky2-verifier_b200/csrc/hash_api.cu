@@ -74,14 +74,6 @@ int p2v_ctx_set_chunk(p2v_ctx *ctx, size_t proofs_per_chunk) {
   return P2V_OK;
 }
 
-int p2v_ctx_last_ms(p2v_ctx *ctx, const char *section, float *ms) {
-  if (!ctx || !section || !ms) return P2V_E_INVALID;
-  auto it = ctx->last_ms.find(section);
-  if (it == ctx->last_ms.end()) return p2v_fail(ctx, P2V_E_INVALID, std::string("no timing for section ") + section);
-  *ms = it->second;
-  return P2V_OK;
-}
-
 int p2v_host_alloc(size_t bytes, void **out) {
   if (!out) return P2V_E_INVALID;
   cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);

@@ -1,0 +1,485 @@
+// C-ABI entry points for circuits and proof batches: p2v_circuit_create, p2v_challenges,
+// p2v_constraints, p2v_fri, p2v_verify_batch, p2v_synth_batch.  See include/p2v.h.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include "constraints.cuh"
+#include "ctx.hpp"
+#include "host/field.hpp"
+
+struct p2v_circuit {
+  p2v_ctx *ctx = nullptr;
+  p2v_shape shape;
+  DevCircuit dev;
+  u64 *d_blob = nullptr;  // vkey | k_is | weights | lut_pairs | tab
+};
+
+namespace {
+
+using namespace p2vhost;
+
+int checkShapeSupported(p2v_ctx *ctx, const p2v_shape &s) {
+  if (s.num_challenges > P2V_MAX_CHALLENGES)
+    return p2v_fail(ctx, P2V_E_UNSUPPORTED, "num_challenges > 4 is not supported");
+  for (int k = 0; k < s.num_gates; k++) {
+    const p2v_gate &g = s.gates[k];
+    switch (g.kind) {
+      case P2V_GATE_UNKNOWN:
+        return p2v_fail(ctx, P2V_E_UNSUPPORTED, "gateConstraints: unknown gate (Gate/Constraints.hs:108)");
+      case P2V_GATE_POSEIDON:
+      case P2V_GATE_POSEIDON_MDS:
+        if (g.p0 != 12) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "gateConstraints/PoseidonGate: unsupported width (Gate/Constraints.hs:93,97)");
+        break;
+      case P2V_GATE_COSET_INTERP:
+        if (g.p0 < 1 || g.p0 > 5 || g.p1 < 2 || g.weights_len != (1 << g.p0))
+          return p2v_fail(ctx, P2V_E_UNSUPPORTED, "CosetInterpolationGate: need 2^subgroup_bits weights, degree >= 2, subgroup_bits <= 5");
+        break;
+      case P2V_GATE_RANDOM_ACCESS:
+        if (g.p0 < 0 || g.p0 > 7) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "RandomAccessGate: bits out of range");
+        break;
+      default: break;
+    }
+  }
+  // every wire / constant index a gate touches must exist (Array `!` raises in the reference)
+  auto need = [&](int k) -> int {
+    const p2v_gate &g = s.gates[k];
+    switch (g.kind) {
+      case P2V_GATE_ARITHMETIC: return 4 * g.p0;
+      case P2V_GATE_ARITHMETIC_EXT: return 8 * g.p0;
+      case P2V_GATE_MUL_EXT: return 6 * g.p0;
+      case P2V_GATE_BASE_SUM: return 1 + g.p0;
+      case P2V_GATE_CONSTANT: return g.p0;
+      case P2V_GATE_PUBLIC_INPUT: return 4;
+      case P2V_GATE_EXPONENTIATION: return 2 * g.p0 + 2;
+      case P2V_GATE_POSEIDON: return 135;
+      case P2V_GATE_POSEIDON_MDS: return 48;
+      case P2V_GATE_RANDOM_ACCESS: return ((2 + (1 << g.p0)) * g.p1 + g.p2 + g.p0 * g.p1);
+      case P2V_GATE_REDUCING: return g.p0 ? 3 * g.p0 + 4 : 0;
+      case P2V_GATE_REDUCING_EXT: return g.p0 ? 4 * g.p0 + 4 : 0;
+      case P2V_GATE_COSET_INTERP: {
+        int np = 1 << g.p0, ni = (np - 2) / (g.p1 - 1);
+        return 1 + 2 * (np + 2) + 4 * ni + 2;
+      }
+      default: return 0;
+    }
+  };
+  for (int k = 0; k < s.num_gates; k++) {
+    if (need(k) > s.num_wires) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "a gate reads a wire beyond num_wires (array index error in the reference)");
+    const p2v_gate &g = s.gates[k];
+    int nconst = g.kind == P2V_GATE_CONSTANT ? g.p0 : g.kind == P2V_GATE_RANDOM_ACCESS ? g.p2 : (g.kind == P2V_GATE_ARITHMETIC || g.kind == P2V_GATE_ARITHMETIC_EXT) ? 2 : g.kind == P2V_GATE_MUL_EXT ? 1 : 0;
+    if (g.p0 > 0 && nconst > s.num_gate_constants) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "a gate reads a constant beyond config.num_constants");
+  }
+  if (s.num_luts > 0 && s.num_lookup_polys < 2) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "lookup tables need at least 2 lookup polynomials");
+  if (s.num_luts > 0 && (s.num_routed_wires / 3 < 1 || 3 * (s.num_routed_wires / 3) > s.num_wires))
+    return p2v_fail(ctx, P2V_E_UNSUPPORTED, "lookup slots exceed the wires");
+  return P2V_OK;
+}
+
+void buildTranscript(DevCircuit &d) {
+  const p2v_layout &L = d.L;
+  int n = 0;
+  auto add = [&](int kind, int off, int count, int dst) {
+    d.ops[n].kind = kind; d.ops[n].off = off; d.ops[n].count = count; d.ops[n].dst = dst;
+    n++;
+  };
+  int r = d.r;
+  // sponge public_inputs (Challenge/Verifier.hs:67)
+  add(TOP_ABSORB_PROOF, L.off_public_inputs, d.num_pi, 0);
+  add(TOP_SPONGE_FINISH, 0, 0, 0);
+  // :73-79
+  add(TOP_ABSORB_VKEY, L.cap_words, 4, 0);
+  add(TOP_ABSORB_PIH, 0, 4, 0);
+  add(TOP_ABSORB_PROOF, L.off_wires_cap, L.cap_words, 0);
+  add(TOP_SQUEEZE, 0, r, d.ch_betas);
+  add(TOP_SQUEEZE, 0, r, d.ch_gammas);
+  if (d.num_lookup_polys > 0) add(TOP_SQUEEZE, 0, 2 * r, d.ch_deltas + 2 * r);  // :82-86
+  add(TOP_ABSORB_PROOF, L.off_zs_pp_cap, L.cap_words, 0);                      // :88-89
+  add(TOP_SQUEEZE, 0, r, d.ch_alphas);
+  add(TOP_ABSORB_PROOF, L.off_quotient_cap, L.cap_words, 0);                   // :91-92
+  add(TOP_SQUEEZE, 0, 2, d.ch_zeta);
+  // friChallenges (Challenge/FRI.hs:73): batch_this = constants ++ sigmas ++ wires ++ zs ++ pp ++ quotient ++ lookup_zs
+  add(TOP_ABSORB_PROOF, L.off_open_constants, 2 * (L.n_open_constants + L.n_open_sigmas + L.n_open_wires + L.n_open_zs), 0);
+  add(TOP_ABSORB_PROOF, L.off_open_pp, 2 * (L.n_open_pp + L.n_open_quotient + L.n_open_lookup_zs), 0);
+  add(TOP_ABSORB_PROOF, L.off_open_zs_next, 2 * L.n_open_zs_next, 0);
+  add(TOP_ABSORB_PROOF, L.off_open_lookup_zs_next, 2 * L.n_open_lookup_zs_next, 0);
+  add(TOP_SQUEEZE, 0, 2, d.ch_fri_alpha);                                      // :76
+  for (int s = 0; s < d.nsteps; s++) {                                         // :79-81
+    add(TOP_ABSORB_PROOF, L.off_commit_caps + s * L.cap_words, L.cap_words, 0);
+    add(TOP_SQUEEZE, 0, 2, d.ch_fri_betas + 2 * s);
+  }
+  add(TOP_ABSORB_PROOF, L.off_final_poly, 2 * d.final_len, 0);                 // :83
+  add(TOP_ABSORB_PROOF, L.off_pow_witness, 1, 0);                              // :89
+  add(TOP_SQUEEZE, 0, 1, d.ch_pow);                                            // :90
+  add(TOP_SQUEEZE, 0, d.Q, d.ch_idx);                                          // :93-97
+  d.nops = n;
+}
+
+struct WsAlloc {
+  Workspace ws;
+  size_t bytes;
+};
+
+// carve the per-chunk planes out of one allocation
+size_t carve(const DevCircuit &d, size_t m, char *base, Workspace *ws, bool want_folded) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return base ? base + o : (char *)nullptr;
+  };
+  u64 *pp = (u64 *)take((size_t)d.L.proof_words * m * 8);
+  u64 *qp = (u64 *)take((size_t)d.L.query_words * d.Q * m * 8);
+  u64 *ch = (u64 *)take((size_t)d.ch_words * m * 8);
+  u64 *pih = (u64 *)take(4 * m * 8);
+  u64 *pre = (u64 *)take(4 * m * 8);
+  u64 *comb = (u64 *)take((size_t)2 * d.r * m * 8);
+  u32 *qstat = (u32 *)take((size_t)d.Q * m * 4);
+  u64 *folded = want_folded ? (u64 *)take((size_t)2 * d.Q * m * 8) : nullptr;
+  uint8_t *eq = (uint8_t *)take(m);
+  if (ws) {
+    ws->pp = pp; ws->qp = qp; ws->ch = ch; ws->pih = pih; ws->pre = pre; ws->comb = comb; ws->qstat = qstat;
+    ws->folded = folded; ws->eqmask = eq;
+  }
+  return off;
+}
+
+int ensureWorkspace(p2v_ctx *ctx, size_t bytes) {
+  if (ctx->ws_bytes >= bytes) return P2V_OK;
+  if (ctx->ws) {
+    P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->ws);
+    ctx->ws = nullptr;
+    ctx->ws_bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&ctx->ws, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return p2v_fail(ctx, P2V_E_NOMEM, "workspace allocation of " + std::to_string(bytes >> 20) + " MiB failed: " + cudaGetErrorString(e) +
+                                          " (lower it with p2v_ctx_set_chunk)");
+  }
+  ctx->ws_bytes = bytes;
+  return P2V_OK;
+}
+
+int ensureStage(p2v_ctx *ctx, size_t bytes) {
+  if (ctx->stage_bytes >= bytes) return P2V_OK;
+  P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  P2V_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  for (auto &b : ctx->stage_buf) {
+    if (b) cudaFree(b);
+    b = nullptr;
+  }
+  ctx->stage_bytes = 0;
+  for (auto &b : ctx->stage_buf) {
+    cudaError_t e = cudaMalloc(&b, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return p2v_fail(ctx, P2V_E_NOMEM, std::string("staging buffer allocation failed: ") + cudaGetErrorString(e));
+    }
+  }
+  ctx->stage_bytes = bytes;
+  return P2V_OK;
+}
+
+enum { RUN_CHALLENGES = 1, RUN_CONSTRAINTS = 2, RUN_FRI = 4 };
+
+struct Outputs {
+  u64 *challenges = nullptr;   // SoA [ch_words][n]
+  u64 *combined = nullptr;     // SoA [2r][n]
+  uint8_t *eqmask = nullptr;   // [n]
+  u32 *status = nullptr;       // [n]
+  u32 *accept_bits = nullptr;  // ceil(n/32)
+  u32 *qstatus = nullptr;      // [n][Q]
+  u64 *folded = nullptr;       // SoA [2][n*Q]
+  int verdict_mode = 0;        // bit0 eqs, bit1 fri
+};
+
+// device-side transposes for the debug outputs
+__global__ void k_copy_planes(const u64 *__restrict__ src, size_t m, int planes, u64 *__restrict__ dst, size_t n_total, size_t c0) {
+  size_t total = (size_t)planes * m;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    size_t pl = i / m, t = i - pl * m;
+    dst[pl * n_total + c0 + t] = src[i];
+  }
+}
+__global__ void k_copy_qstat(const u32 *__restrict__ qstat, size_t m, int Q, u32 *__restrict__ dst, size_t c0) {
+  size_t total = (size_t)Q * m;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    size_t q = i / m, t = i - q * m;
+    dst[(c0 + t) * Q + q] = qstat[i];
+  }
+}
+__global__ void k_copy_folded(const u64 *__restrict__ folded, size_t m, int Q, u64 *__restrict__ dst, size_t n_total, size_t c0) {
+  // src [2][Q*m] with t = q*m + p ; dst [2][n_total*Q] with index p*Q + q
+  size_t total = (size_t)2 * Q * m;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    size_t half = i / ((size_t)Q * m), rem = i - half * (size_t)Q * m;
+    size_t q = rem / m, t = rem - q * m;
+    dst[half * n_total * Q + (c0 + t) * Q + q] = folded[i];
+  }
+}
+__global__ void k_copy_bytes(const uint8_t *__restrict__ src, size_t m, uint8_t *__restrict__ dst) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) dst[i] = src[i];
+}
+__global__ void k_lookup_delta_copies(DevCircuit c, Workspace ws, size_t n) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride)
+    for (int i = 0; i < c.r; i++) {
+      // mkLookupDeltaList (betas ++ gammas ++ deltas), Challenge/Verifier.hs:82-86
+      ws.ch[(size_t)(c.ch_deltas + i) * n + p] = ws.ch[(size_t)(c.ch_betas + i) * n + p];
+      ws.ch[(size_t)(c.ch_deltas + c.r + i) * n + p] = ws.ch[(size_t)(c.ch_gammas + i) * n + p];
+    }
+}
+
+int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t n, int what, Outputs out) {
+  if (!ctx || !cir || !blobs) return p2v_fail(ctx, P2V_E_INVALID, "NULL argument");
+  if (cir->ctx != ctx) return p2v_fail(ctx, P2V_E_INVALID, "circuit belongs to another context");
+  if (n == 0) return P2V_OK;
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  const DevCircuit &d = cir->dev;
+  const size_t blob_words = (size_t)d.L.blob_words;
+  bool src_dev = p2v_is_device_ptr(blobs);
+  size_t chunk = ctx->chunk;
+  if (chunk == 0) {
+    size_t budget = src_dev ? ((size_t)16 << 30) : ((size_t)1 << 30);
+    chunk = budget / (blob_words * 8);
+    if (chunk < 1024) chunk = 1024;
+  }
+  chunk = (chunk + 31) / 32 * 32;
+  if (chunk > n) chunk = (n + 31) / 32 * 32;
+  bool want_folded = out.folded != nullptr;
+  size_t ws_bytes = carve(d, chunk, nullptr, nullptr, want_folded);
+  int rc;
+  if ((rc = ensureWorkspace(ctx, ws_bytes))) return rc;
+  Workspace ws;
+  carve(d, chunk, (char *)ctx->ws, &ws, want_folded);
+  if (!src_dev && (rc = ensureStage(ctx, chunk * blob_words * 8))) return rc;
+
+  // outputs that may live on the host
+  DevOut o_ch, o_comb, o_eq, o_status, o_bits, o_qs, o_folded;
+  if ((rc = o_ch.init(ctx, out.challenges, (size_t)d.ch_words * n * 8))) return rc;
+  if ((rc = o_comb.init(ctx, out.combined, (size_t)2 * d.r * n * 8))) return rc;
+  if ((rc = o_eq.init(ctx, out.eqmask, n))) return rc;
+  if ((rc = o_status.init(ctx, out.status, n * 4))) return rc;
+  if ((rc = o_bits.init(ctx, out.accept_bits, (n + 31) / 32 * 4))) return rc;
+  if ((rc = o_qs.init(ctx, out.qstatus, n * d.Q * 4))) return rc;
+  if ((rc = o_folded.init(ctx, out.folded, (size_t)2 * n * d.Q * 8))) return rc;
+
+  int k = 0;
+  for (size_t c0 = 0; c0 < n; c0 += chunk, k++) {
+    size_t m = std::min(chunk, n - c0);
+    const u64 *src = blobs + c0 * blob_words;
+    int b = k & 1;
+    if (!src_dev) {
+      // double-buffered staging: the H2D copy of chunk k+1 overlaps the kernels of chunk k
+      P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done[b], 0));
+      P2V_CUDA(ctx, cudaMemcpyAsync(ctx->stage_buf[b], src, m * blob_words * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      P2V_CUDA(ctx, cudaEventRecord(ctx->copy_done[b], ctx->copy_stream));
+      P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done[b], 0));
+      src = (const u64 *)ctx->stage_buf[b];
+    }
+    // K0
+    P2V_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    {
+      dim3 grid((unsigned)((blob_words + 31) / 32), (unsigned)((m + 31) / 32));
+      P2V_LAUNCH(ctx, k_stage_transpose, grid, 256, 0, src, m, (int)blob_words, d.L.proof_words, d.L.query_words, d.Q, ws.pp, ws.qp);
+    }
+    if (!src_dev) P2V_CUDA(ctx, cudaEventRecord(ctx->compute_done[b], ctx->stream));
+    P2V_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    // K4
+    P2V_LAUNCH(ctx, k_challenges, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
+    if (d.num_lookup_polys > 0) P2V_LAUNCH(ctx, k_lookup_delta_copies, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m);
+    P2V_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    // K5
+    if (what & RUN_CONSTRAINTS) P2V_LAUNCH(ctx, k_constraints, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
+    P2V_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    // K6
+    if (what & RUN_FRI) P2V_LAUNCH(ctx, k_fri_query, p2v_grid_for(ctx, m * d.Q, 256, 2), 256, 0, d, ws, m);
+    P2V_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    // K7
+    if (out.verdict_mode) {
+      u32 *st = o_status.as<u32>() ? o_status.as<u32>() + c0 : nullptr;
+      u32 *bits = o_bits.as<u32>() ? o_bits.as<u32>() + c0 / 32 : nullptr;
+      P2V_LAUNCH(ctx, k_verdict, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m, out.verdict_mode, st, bits);
+    }
+    P2V_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+    // optional intermediate outputs
+    if (o_ch.dev) P2V_LAUNCH(ctx, k_copy_planes, p2v_grid_for(ctx, m * d.ch_words, 256, 8), 256, 0, ws.ch, m, d.ch_words, o_ch.as<u64>(), n, c0);
+    if (o_comb.dev) P2V_LAUNCH(ctx, k_copy_planes, p2v_grid_for(ctx, m * 2 * d.r, 256, 8), 256, 0, ws.comb, m, 2 * d.r, o_comb.as<u64>(), n, c0);
+    if (o_eq.dev) P2V_LAUNCH(ctx, k_copy_bytes, p2v_grid_for(ctx, m, 256, 8), 256, 0, ws.eqmask, m, o_eq.as<uint8_t>() + c0);
+    if (o_qs.dev) P2V_LAUNCH(ctx, k_copy_qstat, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.qstat, m, d.Q, o_qs.as<u32>(), c0);
+    if (o_folded.dev) P2V_LAUNCH(ctx, k_copy_folded, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.folded, m, d.Q, o_folded.as<u64>(), n, c0);
+  }
+  bool any_host = false;
+  for (DevOut *o : {&o_ch, &o_comb, &o_eq, &o_status, &o_bits, &o_qs, &o_folded}) {
+    if ((rc = o->finish())) return rc;
+    any_host = any_host || (o->host != nullptr);
+  }
+  if (any_host) {
+    P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->last_ms.clear();
+  ctx->last_ms["_pending"] = 1.0f;
+  return P2V_OK;
+}
+
+}  // namespace
+
+// resolve the per-section timings of the last chunk lazily (needs a finished stream)
+static int resolveTimings(p2v_ctx *ctx) {
+  if (ctx->last_ms.count("_pending") == 0) return P2V_OK;
+  P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const char *names[5] = {"stage", "challenges", "constraints", "fri", "verdict"};
+  ctx->last_ms.clear();
+  for (int i = 0; i < 5; i++) {
+    float ms = 0;
+    P2V_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
+    ctx->last_ms[names[i]] = ms;
+  }
+  return P2V_OK;
+}
+
+extern "C" {
+
+int p2v_ctx_last_ms(p2v_ctx *ctx, const char *section, float *ms) {
+  if (!ctx || !section || !ms) return P2V_E_INVALID;
+  int rc = resolveTimings(ctx);
+  if (rc) return rc;
+  auto it = ctx->last_ms.find(section);
+  if (it == ctx->last_ms.end()) return p2v_fail(ctx, P2V_E_INVALID, std::string("no timing for section ") + section);
+  *ms = it->second;
+  return P2V_OK;
+}
+
+int p2v_circuit_create(p2v_ctx *ctx, const p2v_shape *shape, const uint64_t *vkey, p2v_circuit **out) {
+  if (!ctx || !shape || !vkey || !out) return p2v_fail(ctx, P2V_E_INVALID, "p2v_circuit_create: NULL argument");
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = checkShapeSupported(ctx, *shape);
+  if (rc) return rc;
+  p2v_layout L;
+  if ((rc = p2v_shape_layout(shape, &L))) {
+    ctx->err = p2v_tls_error;
+    return rc;
+  }
+  std::unique_ptr<p2v_circuit> c(new p2v_circuit());
+  c->ctx = ctx;
+  c->shape = *shape;
+  c->shape.lut_pairs = nullptr;
+  DevCircuit &d = c->dev;
+  memset(&d, 0, sizeof d);
+  d.L = L;
+  d.num_wires = shape->num_wires; d.num_routed = shape->num_routed_wires; d.num_gate_constants = shape->num_gate_constants;
+  d.r = shape->num_challenges;
+  d.degree_bits = shape->degree_bits; d.rate_bits = shape->rate_bits; d.lde_bits = shape->degree_bits + shape->rate_bits;
+  d.cap_height = shape->cap_height; d.pow_bits = shape->pow_bits; d.Q = shape->num_queries; d.nsteps = shape->num_steps;
+  d.cum_bits[0] = 0;
+  for (int s = 0; s < shape->num_steps; s++) {
+    d.arity_bits[s] = shape->step_arity_bits[s];
+    d.cum_bits[s + 1] = d.cum_bits[s] + shape->step_arity_bits[s];
+    d.inv_arity[s] = hinv((uint64_t)1 << shape->step_arity_bits[s]);
+    d.inv_omega[s] = hinv(hroot(shape->step_arity_bits[s]));
+  }
+  d.final_len = shape->final_poly_len; d.qdf = shape->quotient_degree_factor; d.num_constants = shape->num_constants;
+  d.num_pi = shape->num_public_inputs; d.num_pp = shape->num_partial_products; d.num_lookup_polys = shape->num_lookup_polys;
+  d.num_lookup_sel = shape->num_lookup_selectors; d.num_gates = shape->num_gates; d.num_groups = shape->num_groups;
+  d.num_luts = shape->num_luts;
+  memcpy(d.group_start, shape->group_start, sizeof d.group_start);
+  memcpy(d.group_end, shape->group_end, sizeof d.group_end);
+  memcpy(d.lut_off, shape->lut_off, sizeof d.lut_off);
+  memcpy(d.gates, shape->gates, sizeof d.gates);
+  int r = d.r;
+  d.ch_betas = 0; d.ch_gammas = r; d.ch_alphas = 2 * r; d.ch_deltas = 3 * r;
+  d.ch_zeta = 3 * r + (shape->num_lookup_polys > 0 ? 4 * r : 0);
+  d.ch_fri_alpha = d.ch_zeta + 2; d.ch_fri_betas = d.ch_fri_alpha + 2; d.ch_pow = d.ch_fri_betas + 2 * d.nsteps;
+  d.ch_idx = d.ch_pow + 1; d.ch_words = d.ch_idx + d.Q;
+  d.omega = hroot(d.degree_bits);
+  // device tables
+  size_t n_lut_words = 2 * (size_t)(shape->num_luts ? shape->lut_off[shape->num_luts] : 0);
+  size_t words = (size_t)L.vkey_words + P2V_MAX_ROUTED + P2V_MAX_WEIGHTS + n_lut_words + 128;
+  std::vector<u64> h(words, 0);
+  size_t o_vkey = 0, o_kis = o_vkey + L.vkey_words, o_w = o_kis + P2V_MAX_ROUTED, o_lut = o_w + P2V_MAX_WEIGHTS, o_tab = o_lut + n_lut_words;
+  memcpy(&h[o_vkey], vkey, (size_t)L.vkey_words * 8);
+  memcpy(&h[o_kis], shape->k_is, sizeof shape->k_is);
+  memcpy(&h[o_w], shape->weights, sizeof shape->weights);
+  if (n_lut_words) {
+    if (!shape->lut_pairs) return p2v_fail(ctx, P2V_E_INVALID, "shape has lookup tables but lut_pairs is NULL");
+    memcpy(&h[o_lut], shape->lut_pairs, n_lut_words * 8);
+  }
+  {
+    uint64_t eta = hroot(d.lde_bits), ieta = hinv(eta), g = HGL_MUL_GEN, ig = hinv(g);
+    for (int k = 0; k < 32; k++) {
+      h[o_tab + TAB_ETA + k] = eta; h[o_tab + TAB_INV_ETA + k] = ieta; h[o_tab + TAB_G + k] = g; h[o_tab + TAB_INV_G + k] = ig;
+      eta = hmul(eta, eta); ieta = hmul(ieta, ieta); g = hmul(g, g); ig = hmul(ig, ig);
+    }
+  }
+  P2V_CUDA(ctx, cudaMalloc(&c->d_blob, words * 8));
+  P2V_CUDA(ctx, cudaMemcpy(c->d_blob, h.data(), words * 8, cudaMemcpyHostToDevice));
+  d.vkey = c->d_blob + o_vkey; d.k_is = c->d_blob + o_kis; d.weights = c->d_blob + o_w; d.lut_pairs = c->d_blob + o_lut; d.tab = c->d_blob + o_tab;
+  buildTranscript(d);
+  *out = c.release();
+  return P2V_OK;
+}
+
+void p2v_circuit_destroy(p2v_circuit *c) {
+  if (!c) return;
+  if (c->d_blob) {
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    cudaFree(c->d_blob);
+  }
+  delete c;
+}
+
+int p2v_challenges(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n, uint64_t *challenges_out) {
+  Outputs o;
+  o.challenges = challenges_out;
+  return runBatch(ctx, c, blobs, n, RUN_CHALLENGES, o);
+}
+
+int p2v_constraints(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n, uint64_t *combined_out, uint8_t *eq_ok_mask) {
+  Outputs o;
+  o.combined = combined_out;
+  o.eqmask = eq_ok_mask;
+  return runBatch(ctx, c, blobs, n, RUN_CHALLENGES | RUN_CONSTRAINTS, o);
+}
+
+int p2v_fri(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n, uint32_t *status, uint32_t *query_status, uint64_t *folded_out) {
+  Outputs o;
+  o.status = status;
+  o.qstatus = query_status;
+  o.folded = folded_out;
+  o.verdict_mode = 2;
+  return runBatch(ctx, c, blobs, n, RUN_CHALLENGES | RUN_FRI, o);
+}
+
+int p2v_verify_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n, uint32_t *accept_bits, uint32_t *status) {
+  if (!accept_bits) return p2v_fail(ctx, P2V_E_INVALID, "p2v_verify_batch: accept_bits is NULL");
+  Outputs o;
+  o.status = status;
+  o.accept_bits = accept_bits;
+  o.verdict_mode = 3;
+  return runBatch(ctx, c, blobs, n, RUN_CHALLENGES | RUN_CONSTRAINTS | RUN_FRI, o);
+}
+
+int p2v_synth_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *template_blob, size_t n, const int32_t *tamper_word,
+                    const uint64_t *tamper_delta, uint64_t *blobs_out) {
+  if (!ctx || !c || !template_blob || !blobs_out) return p2v_fail(ctx, P2V_E_INVALID, "p2v_synth_batch: NULL argument");
+  if (!p2v_is_device_ptr(blobs_out)) return p2v_fail(ctx, P2V_E_INVALID, "p2v_synth_batch: blobs_out must be device memory");
+  if ((tamper_word == nullptr) != (tamper_delta == nullptr)) return p2v_fail(ctx, P2V_E_INVALID, "p2v_synth_batch: tamper arrays must come together");
+  if (n == 0) return P2V_OK;
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  int bw = c->dev.L.blob_words;
+  DevIn t, tw, td;
+  int rc;
+  if ((rc = t.init(ctx, template_blob, (size_t)bw * 8))) return rc;
+  if ((rc = tw.init(ctx, tamper_word, n * 4))) return rc;
+  if ((rc = td.init(ctx, tamper_delta, n * 8))) return rc;
+  P2V_LAUNCH(ctx, k_synth, p2v_grid_for(ctx, n * (size_t)bw, 256, 8), 256, 0, t.as<u64>(), bw, n, tw.as<int32_t>(), td.as<u64>(), blobs_out);
+  return P2V_OK;
+}
+
+}  // extern "C"

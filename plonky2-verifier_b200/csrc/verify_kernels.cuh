@@ -1,0 +1,478 @@
+// K0 (stage/transpose), K4 (Fiat-Shamir challenger), K6 (FRI query rounds), K7 (verdict).
+//
+// Data layout in HBM (DESIGN.md "data layout"): a chunk of n proofs arrives as AoS blobs
+// [n][blob_words] (include/p2v.h p2v_layout) and is transposed ONCE by K0 into word planes:
+//   pp[w][n]                 w < proof_words          per-proof part
+//   qp[(w*Q + q)][n]         w < query_words, q < Q   per-query part
+// so that thread t = (q, proof) of every later kernel reads plane[...][proof]: a warp touches 256
+// contiguous bytes per word.  All kernels are shape-generic: the shape lives in a DevCircuit
+// passed by value (kernel parameter space, read through the constant cache).
+#pragma once
+#include "poseidon.cuh"
+#include "../../include/p2v.h"
+
+#define P2V_MAX_CHALLENGES 4
+#define P2V_MAX_TOPS 48
+
+// One operation of the transcript (Challenge/Verifier.hs:73-94, Challenge/FRI.hs:73-97)
+enum { TOP_ABSORB_PROOF = 0, TOP_ABSORB_VKEY = 1, TOP_ABSORB_PIH = 2, TOP_SPONGE_FINISH = 3, TOP_SQUEEZE = 4 };
+struct TOp {
+  int32_t kind, off, count, dst;
+};
+
+struct DevCircuit {
+  p2v_layout L;
+  int32_t num_wires, num_routed, num_gate_constants, r;
+  int32_t degree_bits, rate_bits, lde_bits, cap_height, pow_bits, Q, nsteps;
+  int32_t arity_bits[P2V_MAX_STEPS], cum_bits[P2V_MAX_STEPS + 1];
+  int32_t final_len, qdf, num_constants, num_pi, num_pp, num_lookup_polys, num_lookup_sel;
+  int32_t num_gates, num_groups, num_luts;
+  int32_t group_start[P2V_MAX_GROUPS], group_end[P2V_MAX_GROUPS];
+  int32_t lut_off[P2V_MAX_LUTS + 1];
+  p2v_gate gates[P2V_MAX_GATES];
+  int32_t nops;
+  TOp ops[P2V_MAX_TOPS];
+  // offsets of the challenge planes (include/p2v.h "Challenges of one proof")
+  int32_t ch_betas, ch_gammas, ch_alphas, ch_deltas, ch_zeta, ch_fri_alpha, ch_fri_betas, ch_pow, ch_idx, ch_words;
+  // device-resident tables
+  const u64 *vkey;       // cap [2^cap_height][4] ++ circuit_digest[4]
+  const u64 *k_is;       // [num_routed]
+  const u64 *weights;    // barycentric weights
+  const u64 *lut_pairs;  // (inp,out) pairs
+  const u64 *tab;        // [4][32]: eta^(2^k), eta^-(2^k), g^(2^k), g^-(2^k)   (eta = LDE generator, g = mulGen)
+  u64 omega;             // subgroupGenerator(degree_bits)
+  u64 inv_arity[P2V_MAX_STEPS];  // 1/2^arity_bits
+  u64 inv_omega[P2V_MAX_STEPS];  // subgroupGenerator(arity_bits)^-1
+};
+#define TAB_ETA 0
+#define TAB_INV_ETA 32
+#define TAB_G 64
+#define TAB_INV_G 96
+
+// Per-chunk workspace planes
+struct Workspace {
+  u64 *pp;     // [proof_words][n]
+  u64 *qp;     // [query_words*Q][n]
+  u64 *ch;     // [ch_words][n]   challenges (canonical)
+  u64 *pih;    // [4][n]          sponge(public_inputs)
+  u64 *pre;    // [4][n]          precomputed reduced openings Y0, Y1 (Plonk/FRI.hs:128-134)
+  u64 *comb;   // [2r][n]         combined constraints
+  u32 *qstat;  // [Q][n]          per-query status
+  u64 *folded; // [2][Q*n]        final folded evaluation per query (debug/parity output)
+  uint8_t *eqmask;  // [n]        bit j: round j of the quotient identity holds
+};
+
+__device__ __forceinline__ u32 bitrev(u32 x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
+
+// base^e for a table of base^(2^k): product over the set bits of e
+__device__ __forceinline__ u64 pow_from_table(const u64 *__restrict__ tab, u32 e) {
+  u64 acc = 1;
+  int k = 0;
+  while (e) {
+    if (e & 1u) acc = gl_mul(acc, __ldg(tab + k));
+    e >>= 1;
+    k++;
+  }
+  return acc;
+}
+
+// ---- K0: AoS blobs -> SoA planes -----------------------------------------------------------------
+// 32x32 tiles through shared memory: reads are coalesced along the blob (256 B per proof row),
+// writes are coalesced along the proof index (256 B per word plane).
+__global__ void __launch_bounds__(256) k_stage_transpose(const u64 *__restrict__ blobs, size_t n, int blob_words, int proof_words,
+                                                         int query_words, int Q, u64 *__restrict__ pp, u64 *__restrict__ qp) {
+  __shared__ u64 tile[32][33];
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  size_t p0 = (size_t)blockIdx.y * 32;
+  int w0 = blockIdx.x * 32;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    size_t p = p0 + ty + 8 * k;
+    int w = w0 + tx;
+    if (p < n && w < blob_words) tile[ty + 8 * k][tx] = blobs[p * (size_t)blob_words + w];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int w = w0 + ty + 8 * k;
+    size_t p = p0 + tx;
+    if (p < n && w < blob_words) {
+      u64 v = tile[tx][ty + 8 * k];
+      if (w < proof_words) {
+        pp[(size_t)w * n + p] = v;
+      } else {
+        int rel = w - proof_words;
+        int q = rel / query_words, wq = rel - q * query_words;
+        qp[((size_t)wq * Q + q) * n + p] = v;
+      }
+    }
+  }
+}
+
+// Replicate a template blob n times with one tampered word per copy (synthetic batches).
+__global__ void k_synth(const u64 *__restrict__ tmpl, int blob_words, size_t n, const int32_t *__restrict__ tamper_word,
+                        const u64 *__restrict__ tamper_delta, u64 *__restrict__ out) {
+  size_t total = n * (size_t)blob_words;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    size_t p = i / blob_words;
+    int w = (int)(i - p * blob_words);
+    u64 v = tmpl[w];
+    if (tamper_word && tamper_word[p] == w) v = gl_canon(gl_add(gl_canon(v), gl_canon(tamper_delta[p])));
+    out[i] = v;
+  }
+}
+
+// ---- K4: proofChallenges (Challenge/Verifier.hs:58-103, Challenge/FRI.hs:65-104) ---------------
+// One thread per proof; the duplex sponge of Challenge/Pure.hs:27-69 as an explicit state machine
+// with ONE permutation call site.  Pending inputs / produced outputs live in a tiny local array
+// (dynamic index), the Poseidon state stays in registers.
+__global__ void __launch_bounds__(128) k_challenges(const __grid_constant__ DevCircuit c, Workspace ws, size_t n) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const u64 *__restrict__ pp = ws.pp;
+  u64 s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = 0;
+  u64 buf[8];          // Absorbing: pending inputs; Squeezing: state[0..7] after the last permutation
+  int nbuf = 0;        // Absorbing: number of pending inputs
+  int nout = 0;        // Squeezing: outputs left; next output is buf[nout-1]  (reverse . take 8, Pure.hs:41-43)
+  bool absorbing = true;
+  int pc = 0, sub = 0;  // program counter, position inside the current op
+  for (;;) {
+    bool need_perm = false;
+    // run the transcript until a permutation is required
+    while (pc < c.nops && !need_perm) {
+      TOp op = c.ops[pc];
+      if (op.kind == TOP_SQUEEZE) {
+        if (sub >= op.count) { pc++; sub = 0; continue; }
+        if (absorbing || nout == 0) { need_perm = true; break; }  // Pure.hs:60-69
+        u64 y = gl_canon(buf[nout - 1]);
+        nout--;
+        int dst = op.dst + sub;
+        // query indices: canonical value mod 2^lde_bits (Challenge/FRI.hs:93-97)
+        if (dst >= c.ch_idx) y &= ((1ull << c.lde_bits) - 1);
+        ws.ch[(size_t)dst * n + p] = y;
+        sub++;
+      } else if (op.kind == TOP_SPONGE_FINISH) {
+        // sponge(public_inputs), Hash/Sponge.hs:26-31: flush the last partial block, keep the digest
+        if (absorbing && nbuf > 0) { need_perm = true; break; }
+        // state after the last permutation is in buf[0..7] (or zero if there were no inputs)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          u64 d = (absorbing ? 0 : gl_canon(buf[i]));
+          ws.pih[(size_t)i * n + p] = d;
+        }
+        // runDuplex action zeroState (Challenge/Verifier.hs:59)
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = 0;
+        absorbing = true;
+        nbuf = 0;
+        nout = 0;
+        pc++;
+        sub = 0;
+      } else {
+        if (sub >= op.count) { pc++; sub = 0; continue; }
+        // absorbFelt, Pure.hs:50-58
+        if (!absorbing) { absorbing = true; nbuf = 0; }
+        if (nbuf == 8) { need_perm = true; break; }
+        u64 x;
+        if (op.kind == TOP_ABSORB_PROOF) x = pp[(size_t)(op.off + sub) * n + p];
+        else if (op.kind == TOP_ABSORB_VKEY) x = __ldg(c.vkey + op.off + sub);
+        else x = ws.pih[(size_t)sub * n + p];
+        buf[nbuf++] = x;
+        sub++;
+      }
+    }
+    if (!need_perm) break;
+    if (absorbing) {
+      // duplex inp old = permutation (overwrite inp old), Pure.hs:35-39
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        if (i < nbuf) s[i] = buf[i];
+    }
+    poseidon_permute(s);
+#pragma unroll
+    for (int i = 0; i < 8; i++) buf[i] = s[i];
+    // a permutation triggered by an absorb overflow keeps absorbing; one triggered by a squeeze
+    // (or by the sponge finish) switches to Squeezing with 8 fresh outputs
+    TOp op = c.ops[pc];
+    if (op.kind == TOP_SQUEEZE || op.kind == TOP_SPONGE_FINISH) {
+      absorbing = false;
+      nout = 8;
+    } else {
+      nbuf = 0;
+    }
+  }
+  // precomputeReducedOpenings, Plonk/FRI.hs:128-134: Y0 = sum alpha^i batch_this_i, Y1 over batch_next.
+  // toFriOpenings order (Challenge/FRI.hs:46-61): constants, sigmas, wires, zs, partial_products,
+  // quotient, lookup_zs | zs_next, lookup_zs_next.  Horner from the last element (Goldilocks.hs:180-183).
+  {
+    gl2 alpha = gl2_make(ws.ch[(size_t)c.ch_fri_alpha * n + p], ws.ch[(size_t)(c.ch_fri_alpha + 1) * n + p]);
+    const p2v_layout &L = c.L;
+    int seg_off[7] = {L.off_open_constants, L.off_open_sigmas, L.off_open_wires, L.off_open_zs, L.off_open_pp, L.off_open_quotient, L.off_open_lookup_zs};
+    int seg_n[7] = {L.n_open_constants, L.n_open_sigmas, L.n_open_wires, L.n_open_zs, L.n_open_pp, L.n_open_quotient, L.n_open_lookup_zs};
+    gl2 y0 = gl2_make(0, 0);
+#pragma unroll 1
+    for (int sg = 6; sg >= 0; sg--) {
+#pragma unroll 1
+      for (int i = seg_n[sg] - 1; i >= 0; i--) {
+        gl2 x = gl2_make(pp[(size_t)(seg_off[sg] + 2 * i) * n + p], pp[(size_t)(seg_off[sg] + 2 * i + 1) * n + p]);
+        y0 = gl2_add(x, gl2_mul(alpha, y0));
+      }
+    }
+    int seg2_off[2] = {L.off_open_zs_next, L.off_open_lookup_zs_next};
+    int seg2_n[2] = {L.n_open_zs_next, L.n_open_lookup_zs_next};
+    gl2 y1 = gl2_make(0, 0);
+#pragma unroll 1
+    for (int sg = 1; sg >= 0; sg--) {
+#pragma unroll 1
+      for (int i = seg2_n[sg] - 1; i >= 0; i--) {
+        gl2 x = gl2_make(pp[(size_t)(seg2_off[sg] + 2 * i) * n + p], pp[(size_t)(seg2_off[sg] + 2 * i + 1) * n + p]);
+        y1 = gl2_add(x, gl2_mul(alpha, y1));
+      }
+    }
+    ws.pre[0 * n + p] = gl_canon(y0.a);
+    ws.pre[1 * n + p] = gl_canon(y0.b);
+    ws.pre[2 * n + p] = gl_canon(y1.a);
+    ws.pre[3 * n + p] = gl_canon(y1.b);
+  }
+}
+
+// ---- K6: one FRI query round per thread (checkQueryRound, Plonk/FRI.hs:380-407) ------------------
+// Thread t = (q, proof).  Phase 1: the 4 initial-tree openings and the nsteps coset openings are
+// Merkle-checked through a single permutation call site.  Phase 2: combineInitial, coset folding
+// and the final-polynomial check.  The status keeps the FIRST failure in reference order
+// (SURVEY.md App. E): INIT_MERKLE, then per step STEP_MERKLE, STEP_EVAL, finally FALSE_FINAL.
+__global__ void __launch_bounds__(256, 2) k_fri_query(const __grid_constant__ DevCircuit c, Workspace ws, size_t n) {
+  size_t total = n * (size_t)c.Q;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  const u64 *__restrict__ pp = ws.pp;
+  const u64 *__restrict__ qp = ws.qp;
+  const p2v_layout &L = c.L;
+  const int Q = c.Q;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    int q = (int)(t / n);
+    size_t p = t - (size_t)q * n;
+    const u64 *__restrict__ qbase = qp + (size_t)q * n + p;  // word w of this query at qbase[w*Q*n]
+    const size_t qstride = (size_t)Q * n;
+    u32 idx = (u32)ws.ch[(size_t)(c.ch_idx + q) * n + p];
+
+    // ---------------- phase 1: Merkle openings ----------------
+    u32 init_bad = 0;   // mask of failing initial oracles
+    u32 step_bad = 0;   // mask of failing step trees
+    int ntrees = 4 + c.nsteps;
+#pragma unroll 1
+    for (int tr = 0; tr < ntrees; tr++) {
+      int leaf_off, width, sib_off, plen;
+      u32 index;
+      if (tr < 4) {
+        leaf_off = L.q_off_leaf[tr]; width = L.oracle_width[tr]; sib_off = L.q_off_sibs[tr]; plen = L.init_path_len;
+        index = idx;
+      } else {
+        int st = tr - 4;
+        leaf_off = L.q_off_step_evals[st]; width = 2 << c.arity_bits[st]; sib_off = L.q_off_step_sibs[st]; plen = L.step_path_len[st];
+        index = idx >> c.cum_bits[st + 1];  // query_index_rev newQueryIdx, Plonk/FRI.hs:316
+      }
+      u64 s[12];
+#pragma unroll
+      for (int i = 0; i < 12; i++) s[i] = 0;
+      int nblk = (width + 7) >> 3;
+      int iters = nblk + plen;
+#pragma unroll 1
+      for (int it = 0; it < iters; it++) {
+        if (it < nblk) {
+          // sponge block, Hash/Sponge.hs:26-31 (overwrite the first k lanes)
+          int k = width - it * 8;
+          const u64 *src = qbase + (size_t)(leaf_off + it * 8) * qstride;
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            if (i < k) s[i] = src[(size_t)i * qstride];
+        } else {
+          // compress with the sibling, Hash/Merkle.hs:30-37
+          const u64 *src = qbase + (size_t)(sib_off + (it - nblk) * 4) * qstride;
+          bool even = (index & 1u) == 0;
+          index >>= 1;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            u64 sib = src[(size_t)i * qstride];
+            u64 node = s[i];
+            s[i] = even ? node : sib;
+            s[4 + i] = even ? sib : node;
+            s[8 + i] = 0;
+          }
+        }
+        poseidon_permute(s);
+      }
+      // compare with cap[index] (Merkle.hs:39-42); cap 0 is the verifier key, the others come with the proof
+      bool ok = index < (1u << c.cap_height);
+      u32 ci = ok ? index : 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        u64 want;
+        if (tr == 0) want = __ldg(c.vkey + ci * 4 + i);
+        else {
+          int cap_off = tr == 1 ? L.off_wires_cap : tr == 2 ? L.off_zs_pp_cap : tr == 3 ? L.off_quotient_cap : L.off_commit_caps + (tr - 4) * L.cap_words;
+          want = pp[(size_t)(cap_off + ci * 4 + i) * n + p];
+        }
+        ok = ok && (gl_canon(s[i]) == gl_canon(want));
+      }
+      if (!ok) {
+        if (tr < 4) init_bad |= 1u << tr;
+        else step_bad |= 1u << (tr - 4);
+      }
+    }
+
+    // ---------------- phase 2: combineInitial (Plonk/FRI.hs:151-207) ----------------
+    gl2 alpha = gl2_make(ws.ch[(size_t)c.ch_fri_alpha * n + p], ws.ch[(size_t)(c.ch_fri_alpha + 1) * n + p]);
+    gl2 zeta = gl2_make(ws.ch[(size_t)c.ch_zeta * n + p], ws.ch[(size_t)(c.ch_zeta + 1) * n + p]);
+    int r = c.r;
+    int npp = (c.num_routed + c.qdf - 1) / c.qdf;  // divCeil routed qdf
+    int w2 = L.oracle_width[2];
+    int n_pp = r * npp < w2 ? r * npp : w2;        // splitAt (r*npp)
+    // firstBatch = constants ++ witness ++ oracle_pp ++ quotient ++ oracle_lookup, Horner from the end
+    gl2 g0 = gl2_make(0, 0);
+    {
+      int seg_off[5] = {L.q_off_leaf[0], L.q_off_leaf[1], L.q_off_leaf[2], L.q_off_leaf[3], L.q_off_leaf[2] + n_pp};
+      int seg_n[5] = {L.oracle_width[0], L.oracle_width[1], n_pp, L.oracle_width[3], w2 - n_pp};
+#pragma unroll 1
+      for (int sg = 4; sg >= 0; sg--) {
+#pragma unroll 1
+        for (int i = seg_n[sg] - 1; i >= 0; i--) {
+          u64 x = qbase[(size_t)(seg_off[sg] + i) * qstride];
+          g0 = gl2_add_base(gl2_mul(alpha, g0), x);
+        }
+      }
+    }
+    // secondBatch = take r oracle_pp ++ oracle_lookup
+    gl2 g1 = gl2_make(0, 0);
+    int n_second = 0;
+    {
+      int take_r = r < n_pp ? r : n_pp;
+      int seg_off[2] = {L.q_off_leaf[2], L.q_off_leaf[2] + n_pp};
+      int seg_n[2] = {take_r, w2 - n_pp};
+      n_second = seg_n[0] + seg_n[1];
+#pragma unroll 1
+      for (int sg = 1; sg >= 0; sg--) {
+#pragma unroll 1
+        for (int i = seg_n[sg] - 1; i >= 0; i--) {
+          u64 x = qbase[(size_t)(seg_off[sg] + i) * qstride];
+          g1 = gl2_add_base(gl2_mul(alpha, g1), x);
+        }
+      }
+    }
+    gl2 y0 = gl2_make(ws.pre[0 * n + p], ws.pre[1 * n + p]);
+    gl2 y1 = gl2_make(ws.pre[2 * n + p], ws.pre[3 * n + p]);
+    // point_x = mulGen * eta^rev(idx)
+    u64 point_x = gl_mul(GL_MUL_GEN_C, pow_from_table(c.tab + TAB_ETA, bitrev(idx, c.lde_bits)));
+    gl2 loc1 = gl2_scale(c.omega, zeta);
+    gl2 one = gl2_mul(gl2_sub(g0, y0), gl2_inv(gl2_make(gl_sub(point_x, zeta.a), gl_neg(zeta.b))));
+    gl2 two = gl2_mul(gl2_sub(g1, y1), gl2_inv(gl2_make(gl_sub(point_x, loc1.a), gl_neg(loc1.b))));
+    gl2 apow = gl2_make(1, 0);
+#pragma unroll 1
+    for (int i = 0; i < n_second; i++) apow = gl2_mul(apow, alpha);
+    gl2 eval = gl2_add(gl2_mul(apow, one), two);
+
+    // ---------------- folding steps (Plonk/FRI.hs:306-323) ----------------
+    u32 eval_bad = 0;
+    u32 qidx = idx;
+#pragma unroll 1
+    for (int st = 0; st < c.nsteps; st++) {
+      int a = c.arity_bits[st], A = 1 << a;
+      int bits = c.lde_bits - c.cum_bits[st];
+      const u64 *ev = qbase + (size_t)L.q_off_step_evals[st] * qstride;
+      // evals !! (idx mod arity) == upstream eval  (:317)
+      u32 pos = qidx & (u32)(A - 1);
+      gl2 opened = gl2_make(ev[(size_t)(2 * pos) * qstride], ev[(size_t)(2 * pos + 1) * qstride]);
+      if (!gl2_eq(opened, eval)) eval_bad |= 1u << st;
+      // coset offset ofs = shift * eta_big^rev(bigLog2, (idx>>a)<<a); here its inverse, from the
+      // inverse tables: shift = g^(2^cum), eta_big = eta^(2^cum)   (prepareCoset :248-259)
+      u32 start = bitrev((qidx >> a) << a, bits);
+      u64 inv_ofs = gl_mul(__ldg(c.tab + TAB_INV_G + c.cum_bits[st]), pow_from_table(c.tab + TAB_INV_ETA + c.cum_bits[st], start));
+      // foldCosetWith (:263-279): (1/A) sum_k beta^k sum_j (ofs w^j)^-k v_j  =  (1/A) sum_j v_j S(t_j),
+      // t_j = beta/(ofs w^j),  S(t) = sum_{k<A} t^k = prod_{i<a} (1 + t^(2^i));  v = bit-reversed evals
+      gl2 beta = gl2_make(ws.ch[(size_t)(c.ch_fri_betas + 2 * st) * n + p], ws.ch[(size_t)(c.ch_fri_betas + 2 * st + 1) * n + p]);
+      gl2 tj = gl2_scale(inv_ofs, beta);
+      u64 inv_w = c.inv_omega[st];
+      gl2 acc = gl2_make(0, 0);
+#pragma unroll 1
+      for (int j = 0; j < A; j++) {
+        u32 src = bitrev((u32)j, a);
+        gl2 v = gl2_make(ev[(size_t)(2 * src) * qstride], ev[(size_t)(2 * src + 1) * qstride]);
+        gl2 S = gl2_make(1, 0), tp = tj;
+#pragma unroll 1
+        for (int i = 0; i < a; i++) {
+          S = gl2_mul(S, gl2_add_base(tp, 1));
+          tp = gl2_sqr(tp);
+        }
+        acc = gl2_add(acc, gl2_mul(v, S));
+        tj = gl2_scale(inv_w, tj);
+      }
+      eval = gl2_scale(c.inv_arity[st], acc);
+      qidx >>= a;
+    }
+    // ---------------- final polynomial (:288-291, 325-327, 404-407) ----------------
+    int cum = c.cum_bits[c.nsteps];
+    int fbits = c.lde_bits - cum;
+    u64 x_final = gl_mul(__ldg(c.tab + TAB_G + cum), pow_from_table(c.tab + TAB_ETA + cum, bitrev(qidx, fbits)));
+    gl2 fpe = gl2_make(0, 0);
+#pragma unroll 1
+    for (int i = c.final_len - 1; i >= 0; i--) {
+      gl2 co = gl2_make(pp[(size_t)(L.off_final_poly + 2 * i) * n + p], pp[(size_t)(L.off_final_poly + 2 * i + 1) * n + p]);
+      fpe = gl2_add(gl2_scale(x_final, fpe), co);
+    }
+    bool final_ok = gl2_eq(fpe, eval);
+
+    // ---------------- status in reference order ----------------
+    u32 status = P2V_ST_ACCEPT;
+    if (init_bad) status = P2V_ST_ERR_INIT_MERKLE | (init_bad << 16);
+    else {
+      bool decided = false;
+#pragma unroll 1
+      for (int st = 0; st < c.nsteps && !decided; st++) {
+        if (step_bad & (1u << st)) { status = P2V_ST_ERR_STEP_MERKLE | ((u32)st << 16); decided = true; }
+        else if (eval_bad & (1u << st)) { status = P2V_ST_ERR_STEP_EVAL | ((u32)st << 16); decided = true; }
+      }
+      if (!decided && !final_ok) status = P2V_ST_FALSE_FINAL;
+    }
+    if (status != P2V_ST_ACCEPT) status |= (u32)q << 8;
+    ws.qstat[t] = status;
+    if (ws.folded) {
+      gl2 ce = gl2_canon(eval);
+      ws.folded[t] = ce.a;
+      ws.folded[total + t] = ce.b;
+    }
+  }
+}
+
+// ---- K7: verdict (verifyProof, Plonk/Verifier.hs:56-65; checkFRIProof `ok`, Plonk/FRI.hs:370-372) --
+// mode bit 0: include the quotient-identity check; bit 1: include the FRI part.
+__global__ void __launch_bounds__(256) k_verdict(const __grid_constant__ DevCircuit c, Workspace ws, size_t n, int mode,
+                                                 u32 *__restrict__ status_out, u32 *__restrict__ accept_bits) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t n_round = (n + 31) / 32 * 32;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += stride) {
+    bool live = t < n;
+    size_t p = live ? t : n - 1;
+    u32 status = P2V_ST_ACCEPT;
+    bool decided = false;
+    if (mode & 1) {
+      u32 ok = ws.eqmask[p];
+      u32 all = (1u << c.r) - 1;
+      if ((ok & all) != all) { status = P2V_ST_FALSE_EQS | ((~ok & all) << 16); decided = true; }
+    }
+    if (!decided && (mode & 2)) {
+      // checkProofOfWork, Plonk/FRI.hs:212-216: the top pow_bits of the canonical response are zero
+      u64 resp = ws.ch[(size_t)c.ch_pow * n + p];
+      bool pow_ok = c.pow_bits == 0 || (resp >> (64 - c.pow_bits)) == 0;
+      if (!pow_ok) { status = P2V_ST_FALSE_POW; decided = true; }
+      for (int q = 0; q < c.Q && !decided; q++) {
+        u32 qs = ws.qstat[(size_t)q * n + p];
+        if (qs != P2V_ST_ACCEPT) { status = qs; decided = true; }
+      }
+    }
+    if (live && status_out) status_out[p] = status;
+    u32 ballot = __ballot_sync(0xffffffffu, live && status == P2V_ST_ACCEPT);
+    if (accept_bits && (threadIdx.x & 31) == 0) accept_bits[t / 32] = ballot;
+  }
+}

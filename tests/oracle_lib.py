@@ -66,6 +66,59 @@ class Oracle:
     def perm_loop(self, iters, threads, which=2):
         return self.lib.orc_perm_loop(iters, threads, which)
 
+    def verify_batch(self, shape, vkey, blobs, threads=8, fast=True):
+        """Restatement of verifyProof (+ all intermediates) on a batch of flat blobs.
+        Returns a dict: challenges [cw][n], combined [2r][n], eqmask, status, fri_status, qstatus [n][Q],
+        folded [2][n*Q], perms."""
+        import plonky2_verifier_b200 as p2v
+
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint64)
+        if blobs.ndim == 1:
+            blobs = blobs.reshape(1, -1)
+        n = blobs.shape[0]
+        vkey = np.ascontiguousarray(vkey, dtype=np.uint64)
+        cw = challenges_words_py(shape)
+        Q, r = shape.num_queries, shape.num_challenges
+        out = dict(
+            challenges=np.zeros((cw, n), dtype=np.uint64), combined=np.zeros((2 * r, n), dtype=np.uint64),
+            eqmask=np.zeros(n, dtype=np.uint8), status=np.zeros(n, dtype=np.uint32),
+            fri_status=np.zeros(n, dtype=np.uint32), qstatus=np.zeros((n, Q), dtype=np.uint32),
+            folded=np.zeros((2, n * Q), dtype=np.uint64))
+        perms = C.c_ulonglong(0)
+        fn = self.lib.orc_verify_batch
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]
+        fn(C.addressof(shape), vkey.ctypes.data, blobs.ctypes.data, n, threads, 1 if fast else 0,
+           out["challenges"].ctypes.data, out["combined"].ctypes.data, out["eqmask"].ctypes.data,
+           out["status"].ctypes.data, out["fri_status"].ctypes.data, out["qstatus"].ctypes.data,
+           out["folded"].ctypes.data, C.addressof(perms))
+        out["perms"] = perms.value
+        return out
+
+    def gate_constraints(self, shape, gate_index, wires, consts, pih, max_out=256):
+        wires = np.ascontiguousarray(wires, dtype=np.uint64)
+        consts = np.ascontiguousarray(consts, dtype=np.uint64)
+        pih = np.ascontiguousarray(pih, dtype=np.uint64)
+        out = np.zeros((max_out, 2), dtype=np.uint64)
+        fn = self.lib.orc_gate_constraints
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        k = fn(C.addressof(shape), gate_index, wires.ctypes.data, wires.shape[0], consts.ctypes.data, consts.shape[0],
+               pih.ctypes.data, out.ctypes.data, max_out)
+        if k < 0:
+            raise RuntimeError("oracle raised while evaluating the gate")
+        return out[:k]
+
+    def blob_words(self, shape, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint64)
+        fn = self.lib.orc_blob_words
+        fn.argtypes = [C.c_void_p, C.c_void_p]
+        fn.restype = C.c_size_t
+        return fn(C.addressof(shape), blob.ctypes.data)
+
+
+def challenges_words_py(shape):
+    r = shape.num_challenges
+    return 3 * r + (4 * r if shape.num_lookup_polys > 0 else 0) + 4 + 2 * shape.num_steps + 1 + shape.num_queries
+
 
 _cached = None
 

@@ -1,0 +1,95 @@
+"""GPU parity: K0 + K4-K7 through the C ABI vs the CPU oracle on the bundled fixtures and on
+tampered copies (bit-exact challenges, combined constraints, folded evaluations, verdict codes)."""
+import numpy as np
+import pytest
+
+import fixtures
+
+pytestmark = pytest.mark.gpu
+
+
+def _circuit(p2v, ctx, name):
+    shape, lay, vkey, blob = fixtures.load(name)
+    return p2v.Circuit(ctx, shape, vkey), shape, lay, vkey, blob
+
+
+@pytest.mark.parametrize("name", fixtures.ACCEPTING)
+def test_fixture_accepts_and_intermediates_match(p2v, ctx, orc, name):
+    cir, shape, lay, vkey, blob = _circuit(p2v, ctx, name)
+    blobs = blob.reshape(1, -1)
+    want = orc.verify_batch(shape, vkey, blobs, threads=1, fast=False)
+    assert want["status"][0] == 0, "oracle must accept the bundled fixture"
+    ch = cir.proofChallenges(blobs)
+    assert np.array_equal(ch, want["challenges"])
+    comb, mask = cir.evalCombinedPlonkConstraints(blobs)
+    assert np.array_equal(comb, want["combined"])
+    assert mask[0] == want["eqmask"][0] == (1 << shape.num_challenges) - 1
+    st, qs, folded = cir.checkFRIProof(blobs, want_debug=True)
+    assert st[0] == 0 and (qs == 0).all()
+    assert np.array_equal(folded, want["folded"])
+    acc, status = cir.verifyProof(blobs)
+    assert acc[0] and status[0] == 0
+
+
+@pytest.mark.parametrize("name,code", [("small6_badfinal", 3), ("small6_badlayer0", 18), ("small6_badlayer1", 18 | (1 << 16))])
+def test_regrinded_rejections(p2v, ctx, orc, name, code):
+    """Proofs that reach the deep checks (need prover-side re-grinding): FALSE_FINAL, ERR_STEP_EVAL."""
+    cir, shape, lay, vkey, blob = _circuit(p2v, ctx, name)
+    blobs = blob.reshape(1, -1)
+    want = orc.verify_batch(shape, vkey, blobs, threads=1, fast=False)
+    acc, status = cir.verifyProof(blobs)
+    assert status[0] == want["status"][0] == code
+    assert not acc[0]
+    st, qs, folded = cir.checkFRIProof(blobs, want_debug=True)
+    assert np.array_equal(qs, want["qstatus"])
+    assert np.array_equal(folded, want["folded"])
+
+
+@pytest.mark.parametrize("name,n", [("small6", 96), ("fixed4", 80), ("lookup6", 96), ("mid5", 64), ("s12", 48)])
+def test_tamper_matrix(p2v, ctx, orc, name, n):
+    cir, shape, lay, vkey, blob = _circuit(p2v, ctx, name)
+    blobs, words, deltas = fixtures.tampered_batch(blob, lay, shape, n, seed=7)
+    want = orc.verify_batch(shape, vkey, blobs, threads=8, fast=True)
+    assert (want["status"] != 0xEE).all()
+    ch = cir.proofChallenges(blobs)
+    assert np.array_equal(ch, want["challenges"])
+    comb, mask = cir.evalCombinedPlonkConstraints(blobs)
+    assert np.array_equal(comb, want["combined"])
+    assert np.array_equal(mask, want["eqmask"])
+    st, qs, folded = cir.checkFRIProof(blobs, want_debug=True)
+    assert np.array_equal(qs, want["qstatus"])
+    assert np.array_equal(st, want["fri_status"])
+    # folded evaluations only compared where the oracle got that far (it raises at the first failure)
+    ok_rounds = (want["qstatus"] == 0) | ((want["qstatus"] & 0xFF) == 3)
+    f_g = folded.reshape(2, n, shape.num_queries)
+    f_o = want["folded"].reshape(2, n, shape.num_queries)
+    assert np.array_equal(f_g[:, ok_rounds], f_o[:, ok_rounds])
+    acc, status = cir.verifyProof(blobs)
+    assert np.array_equal(status, want["status"])
+    assert np.array_equal(acc, want["status"] == 0)
+    # untouched copies accept, every class of rejection shows up
+    assert acc[words < 0].all()
+    codes = set(int(s) & 0xFF for s in status)
+    assert {0, 1, 2, 16, 17} <= codes, codes
+
+
+def test_chunked_and_device_resident(p2v, ctx, orc):
+    """Same verdicts when the batch is split into chunks and when it already lives in HBM."""
+    import torch
+
+    cir, shape, lay, vkey, blob = _circuit(p2v, ctx, "small6")
+    n = 200
+    blobs, words, deltas = fixtures.tampered_batch(blob, lay, shape, n, seed=3)
+    acc0, st0 = cir.verifyProof(blobs)
+    ctx.set_chunk(64)
+    acc1, st1 = cir.verifyProof(blobs)
+    d_blobs = torch.from_numpy(blobs.view(np.int64)).cuda()
+    acc2, st2 = cir.verifyProof(d_blobs, n=n)
+    ctx.set_chunk(0)
+    assert np.array_equal(st0, st1) and np.array_equal(st0, st2)
+    assert np.array_equal(acc0, acc1) and np.array_equal(acc0, acc2)
+    # device-side synthesis gives the same batch
+    d_out = torch.empty((n, lay.blob_words), dtype=torch.int64, device="cuda")
+    cir.synth_batch(blob, n, words, deltas, d_out)
+    ctx.sync()
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint64), blobs)
