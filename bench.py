@@ -1,0 +1,346 @@
+#!/usr/bin/env python3
+"""bench.py — throughput of the batch Plonky2 verifier on B200 (contract: see the task's bench.py section).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--proofs B] [--impl reference]
+
+Workload (BASELINE.json configs[3]/[4]): full verification (challenges + constraints + FRI) of B
+standard-recursion-shape proofs per GPU.  The batch is synthetic: the bundled accepting S12 fixture
+(tests/golden/s12_*.json) replicated B times, 3 out of 4 copies tampered in one word (the schedule
+of tests/fixtures.py).  A "step" is one pass of the hot path over that batch.
+
+  value : proofs/s with the AoS blobs already resident in HBM (timed: K0 stage + K4 + K5 + K6 + K7)
+  e2e   : proofs/s through p2v_verify_batch with HOST (pinned) buffers: H2D of the blobs and D2H of the
+          accept bitmap + status words are inside the timed region
+  roofline : integer pipe (IMAD.WIDE.U32), achieved = permutations/s of the dominant kernel x 6376
+              against the IMAD.WIDE peak measured live on this GPU; plus achieved HBM GB/s
+  cpu_baseline : the CPU oracle (C++ restatement, "port") on the host cores over a bounded sample
+
+Multi-GPU (torchrun, one rank per GPU): contiguous equal slices, no data-path collective, one NCCL
+all_gather of the accept bitmap inside the timed region; weak scaling (B proofs per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+IMADS_PER_PERM = 6376  # 32x32->64 multiplies per permutation (fast-partial formulation)
+METRIC = "proofs_verified_per_sec"
+UNIT = "proofs/s"
+
+
+def perms_per_proof(shape, lay):
+    """Permutation count of one verification at this shape (commentary/FRI.md:250-267)."""
+    c = lambda w: (w + 7) // 8
+    per_query = sum(c(lay.oracle_width[o]) + lay.init_path_len for o in range(4))
+    for s in range(shape.num_steps):
+        per_query += c(2 << shape.step_arity_bits[s]) + lay.step_path_len[s]
+    return per_query  # challenger perms are added by the caller (counted by the oracle)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(shape, lay, vkey, blobs, seconds=12.0):
+    """The oracle (kind 'port') over a bounded sample of the same batch, all host threads."""
+    import oracle_lib
+
+    orc = oracle_lib.load()
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    probe = orc.verify_batch(shape, vkey, blobs[:cores], threads=cores, fast=True)
+    dt = max(time.time() - t0, 1e-3)
+    sample = int(min(len(blobs), max(cores, cores * round(seconds / dt))))
+    sample -= sample % cores
+    t0 = time.time()
+    res = orc.verify_batch(shape, vkey, blobs[:sample], threads=cores, fast=True)
+    dt = time.time() - t0
+    return {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d proofs of the same batch (%.1f s of wall time on %d threads; C++ restatement of the Haskell "
+                      "reference, which cannot be built here: no GHC)" % (sample, dt, cores),
+            "perms_per_s": res["perms"] / dt}, res, sample
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (no GHC in the image)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    import fixtures
+    import plonky2_verifier_b200 as p2v  # host parser only (JSON -> blob); no GPU call is made in this arm
+
+    shape, lay, vkey, blob = fixtures.load("s12")
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 2 * cores)
+    blobs, _, _ = fixtures.tampered_batch(blob, lay, shape, per_step, seed=11)
+    import oracle_lib
+
+    orc = oracle_lib.load()
+    for _ in range(args.warmup):
+        orc.verify_batch(shape, vkey, blobs[:cores], threads=cores, fast=True)
+    t0 = time.time()
+    for _ in range(args.steps):
+        orc.verify_batch(shape, vkey, blobs, threads=cores, fast=True)
+    dt = time.time() - t0
+    value = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "full verifier on standard-recursion-shape (S12) proofs", "proofs_per_step": per_step,
+                   "note": "CPU arm: C++ restatement of the Haskell reference on all host threads (GHC is not in the image)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": "%d proofs per step" % per_step},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--proofs", type=int, default=100000, help="proofs per GPU per step")
+    ap.add_argument("--e2e-proofs", type=int, default=0, help="proofs per GPU for the host-buffer measurement (0 = auto)")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import fixtures
+    import plonky2_verifier_b200 as p2v
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: libp2v has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    shape, lay, vkey, blob = fixtures.load("s12")
+    ctx = p2v.Context(local_rank)
+    cir = p2v.Circuit(ctx, shape, vkey)
+    n = args.proofs
+    W = lay.blob_words
+    stream = torch.cuda.ExternalStream(ctx.stream)
+
+    # ---- synthetic batch: schedule of tests/fixtures.py, built on the device from the parsed template ----
+    sched_blobs, words, deltas = fixtures.tampered_batch(blob, lay, shape, min(n, 4096), seed=1000 + rank)
+    reps = (n + len(words) - 1) // len(words)
+    words_n = np.tile(words, reps)[:n].copy()
+    deltas_n = np.tile(deltas, reps)[:n].copy()
+    d_blobs = torch.empty((n, W), dtype=torch.int64, device="cuda")
+    cir.synth_batch(blob, n, words_n, deltas_n, d_blobs)
+    n_words = (n + 31) // 32
+    d_bits = torch.zeros(n_words, dtype=torch.int32, device="cuda")
+    d_status = torch.zeros(n, dtype=torch.int32, device="cuda")
+    gathered = torch.zeros(n_words * world, dtype=torch.int32, device="cuda") if world > 1 else None
+    ctx.sync()
+
+    def step_device():
+        cir.verifyProof(d_blobs, n=n, accept_bits=d_bits, status=d_status)
+        if dist is not None:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered, d_bits)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # int-pipe peak on this GPU, measured before the timed region
+    imad_peak = ctx.int_pipe_peak(0)
+
+    for _ in range(max(args.warmup, 3) if args.warmup >= 0 else 3):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record()
+    for _ in range(args.steps):
+        step_device()
+    with torch.cuda.stream(stream):
+        e1.record()
+    e1.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    ms_total = e0.elapsed_time(e1)
+    fri_ms = ctx.last_ms("fri")
+    sec_ms = {k: ctx.last_ms(k) for k in ("stage", "challenges", "constraints", "fri", "verdict")}
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = n * world / (ms_per_step * 1e-3)
+
+    # ---- correctness of what was timed: verdicts of a prefix vs the oracle (rank 0, outside the timing) ----
+    status_host = d_status.cpu().numpy().view(np.uint32)
+    accept_host = p2v.unpack_bits(d_bits.cpu().numpy().view(np.uint32), n)
+    assert np.array_equal(accept_host, status_host == 0)
+    if dist is not None:
+        g = gathered.cpu().numpy().view(np.uint32).reshape(world, n_words)
+        assert np.array_equal(g[rank], d_bits.cpu().numpy().view(np.uint32)), "allgather returned a different bitmap"
+
+    # ---- e2e: host buffers through the C ABI ----
+    import psutil
+
+    avail = psutil.virtual_memory().available
+    n_e2e = args.e2e_proofs or n
+    while n_e2e * W * 8 * 3 > avail and n_e2e > 1024:
+        n_e2e //= 2
+    h_blobs_t = torch.empty((n_e2e, W), dtype=torch.int64, pin_memory=True)
+    h_blobs = h_blobs_t.numpy().view(np.uint64)
+    src = d_blobs[:n_e2e].cpu().numpy().view(np.uint64)
+    h_blobs[:] = src
+    del src
+    h_bits_t = torch.zeros((n_e2e + 31) // 32, dtype=torch.int32, pin_memory=True)
+    h_status_t = torch.zeros(n_e2e, dtype=torch.int32, pin_memory=True)
+    h_bits, h_status = h_bits_t.numpy().view(np.uint32), h_status_t.numpy().view(np.uint32)
+
+    def step_host():
+        cir.verifyProof(h_blobs, n=n_e2e, accept_bits=h_bits, status=h_status)  # synchronous: outputs are host buffers
+
+    for _ in range(2):
+        step_host()
+    barrier()
+    e2e_steps = max(2, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n_e2e * world * e2e_steps / float(te.item())
+    assert np.array_equal(h_status, status_host[:n_e2e]), "host-buffer path and device-resident path disagree"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (k_fri_query) ----
+    ppq = perms_per_proof(shape, lay)
+    fri_perms = n * shape.num_queries * ppq
+    perms_per_s = fri_perms / (fri_ms * 1e-3)
+    achieved = perms_per_s * IMADS_PER_PERM
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "measured" if "hbm_gbs" in peaks else "fallback"
+    algo_bytes = n * W * 8 * 2 + n * W * 8  # K0 reads AoS + writes SoA, later kernels read the planes once
+    hbm_achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu, cpu_res, sample = cpu_baseline(shape, lay, vkey, sched_blobs)
+        # the sample is also a parity check of the timed batch (same schedule => same verdicts)
+        assert np.array_equal(cpu_res["status"], status_host[:sample]), "GPU verdicts differ from the CPU oracle"
+
+    hist = {}
+    for s in status_host:
+        hist[int(s) & 0xFF] = hist.get(int(s) & 0xFF, 0) + 1
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": "full verifier (challenges + constraints + FRI) on standard-recursion-shape (S12) proofs",
+                   "proofs_per_gpu": n, "blob_bytes": W * 8, "queries": shape.num_queries, "perms_per_proof": 114 + shape.num_queries * ppq,
+                   "l2": "inputs (%.1f GB per step) are far larger than L2" % (n * W * 8 / 1e9),
+                   "batch": "bundled S12 fixture x %d, 3 of 4 copies tampered in one word" % n,
+                   "verdict_histogram": hist, "multi_gpu": "contiguous slices + NCCL all_gather of the accept bitmap" if world > 1 else "single GPU"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * W * 8, "d2h_bytes_per_step": int(h_bits.nbytes + h_status.nbytes),
+                "proofs_per_gpu": n_e2e},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "int_pipe", "kernel": "k_fri_query", "achieved": achieved / 1e9, "peak": imad_peak / 1e9, "unit": "GIMAD/s",
+                     "frac": achieved / imad_peak, "traffic": None, "perms_per_s": perms_per_s, "kernel_ms": fri_ms,
+                     "peak_source": "IMAD.WIDE.U32 microbenchmark run live on this GPU (p2v_int_pipe_peak)",
+                     "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                             "peak_source": hbm_src + " copy bandwidth (MEASURED_PEAKS.json)"}},
+        "kernel_ms": sec_ms,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -89,7 +89,7 @@ def tampered_batch(blob, lay, shape, n, seed=0, accept_every=4):
             deltas[i] = 1
         else:
             words[i] = rng.integers(0, lay.blob_words)
-            deltas[i] = rng.integers(1, P)
+            deltas[i] = rng.integers(1, P, dtype=np.uint64)
         k += 1
     blobs = np.tile(np.asarray(blob, dtype=np.uint64), (n, 1))
     for i in range(n):

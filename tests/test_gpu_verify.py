@@ -42,7 +42,10 @@ def test_regrinded_rejections(p2v, ctx, orc, name, code):
     assert not acc[0]
     st, qs, folded = cir.checkFRIProof(blobs, want_debug=True)
     assert np.array_equal(qs, want["qstatus"])
-    assert np.array_equal(folded, want["folded"])
+    # the oracle raises at the first failing check of a round, so it has folded values only for
+    # rounds that ran to the final-polynomial comparison
+    done = ((want["qstatus"] == 0) | ((want["qstatus"] & 0xFF) == 3)).reshape(-1)
+    assert np.array_equal(folded[:, done], want["folded"][:, done])
 
 
 @pytest.mark.parametrize("name,n", [("small6", 96), ("fixed4", 80), ("lookup6", 96), ("mid5", 64), ("s12", 48)])
