@@ -265,9 +265,9 @@ int p2v_synth_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *template
                     const int32_t *tamper_word, const uint64_t *tamper_delta, uint64_t *blobs_out);
 
 /* ---- measurement helpers ------------------------------------------------------- */
-/* Integer-pipe peak microbenchmark: dependent chains of IMAD.WIDE.U32 (mode 0), IMAD (mode 1),
- * IADD3 (mode 2), LOP3 (mode 3), IMAD.WIDE+IADD3 interleaved (mode 4).  Returns warp-level
- * instructions/s * 32 (thread ops per second) in *ops_per_s. */
+/* Integer-pipe peak microbenchmark: dependent chains whose every step is a GROUP of instructions:
+ * mode 0: LOP3 + IMAD.WIDE.U32, 1: 2 LOP3 + IMAD.WIDE.U32, 2: LOP3 + IMAD (32-bit), 3: LOP3 + IADD3,
+ * 4: 2 IMAD.WIDE.U32 + LOP3.  *ops_per_s = groups per second summed over all threads. */
 int p2v_int_pipe_peak(p2v_ctx *ctx, int mode, double *ops_per_s);
 /* Time of the most recent timed section in ms, by name ("stage","challenges","constraints","fri","verdict"). */
 int p2v_ctx_last_ms(p2v_ctx *ctx, const char *section, float *ms);

@@ -247,7 +247,7 @@ int p2v_int_pipe_peak(p2v_ctx *ctx, int mode, double *ops_per_s) {
     if (rep > 0 && ms < best) best = ms;
   }
   cudaFree(d);
-  double per_thread = (double)iters * 64.0 * (mode == 4 ? 2.0 : 1.0);
+  double per_thread = (double)iters * 64.0;  // groups per thread
   *ops_per_s = per_thread * (double)grid * block / (best * 1e-3);
   return P2V_OK;
 }

@@ -147,18 +147,22 @@ __global__ void k_cap_transpose(const u64 *__restrict__ level, u32 ncap, u64 *__
 }
 
 // ---- integer-pipe peak microbenchmark (measurement helper) --------------------------------
-// mode 0: IMAD.WIDE.U32 chains, 1: IMAD (32-bit) chains, 2: IADD3 chains, 3: LOP3 chains,
-// mode 4: IMAD.WIDE.U32 and IADD3 interleaved 1:1.  8 independent chains per thread.
+// 8 independent dependent-chains per thread; every step of a chain is a GROUP of instructions:
+//   mode 0: LOP3 + IMAD.WIDE.U32   (both halves of the product feed the next step, so ptxas cannot
+//                                   narrow it to a 32-bit IMAD or hoist it)
+//   mode 1: LOP3 + LOP3 + IMAD.WIDE.U32
+//   mode 2: LOP3 + IMAD (32-bit mul.lo)
+//   mode 3: LOP3 + IADD3           (ALU pipe only)
+//   mode 4: IMAD.WIDE.U32 + IMAD.WIDE.U32 + LOP3
+// p2v_int_pipe_peak reports GROUPS per second (x32 threads).  If IMAD.WIDE issues every 2 cycles per
+// SM sub-partition, modes 0, 2 and 3 give the same rate (64 groups/clk/SM); mode 4 then runs at half
+// that rate, and if IMAD.WIDE were half rate mode 0 would already be at half.
 template <int MODE>
 __global__ void __launch_bounds__(256) k_int_pipe(u64 *out, u32 iters, u32 seed) {
   u32 x = threadIdx.x * 2654435761u + seed;
   u64 a[8];
-  u32 b[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    a[i] = x + i;
-    b[i] = x * (i + 3);
-  }
+  for (int i = 0; i < 8; i++) a[i] = (u64)x * (i + 3) + i;
 #pragma unroll 1
   for (u32 it = 0; it < iters; it++) {
 #pragma unroll
@@ -166,22 +170,21 @@ __global__ void __launch_bounds__(256) k_int_pipe(u64 *out, u32 iters, u32 seed)
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         if (MODE == 0) {
-          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(b[i]), "r"(x));
+          asm volatile("{.reg .u32 lo,hi,t; mov.b64 {lo,hi},%0; xor.b32 t,lo,hi; mul.wide.u32 %0,t,%1;}" : "+l"(a[i]) : "r"(x));
         } else if (MODE == 1) {
-          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(b[i]) : "r"(x), "r"(seed));
+          asm volatile("{.reg .u32 lo,hi,t; mov.b64 {lo,hi},%0; xor.b32 t,lo,hi; and.b32 t,t,%1; mul.wide.u32 %0,t,%1;}" : "+l"(a[i]) : "r"(x));
         } else if (MODE == 2) {
-          asm volatile("add.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(x));
+          asm volatile("{.reg .u32 lo,hi,t; mov.b64 {lo,hi},%0; xor.b32 t,lo,%1; mul.lo.u32 lo,t,%1; mov.b64 %0,{lo,hi};}" : "+l"(a[i]) : "r"(x));
         } else if (MODE == 3) {
-          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[i]) : "r"(x), "r"(seed));
+          asm volatile("{.reg .u32 lo,hi,t; mov.b64 {lo,hi},%0; xor.b32 t,lo,%1; add.u32 lo,lo,t; mov.b64 %0,{lo,hi};}" : "+l"(a[i]) : "r"(x));
         } else {
-          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(b[i]), "r"(x));
-          asm volatile("add.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(seed));
+          asm volatile("{.reg .u32 lo,hi,t; .reg .u64 w; mov.b64 {lo,hi},%0; xor.b32 t,lo,hi; mul.wide.u32 w,t,%1; mov.b64 {lo,hi},w; mul.wide.u32 %0,lo,hi;}" : "+l"(a[i]) : "r"(x));
         }
       }
     }
   }
   u64 acc = 0;
 #pragma unroll
-  for (int i = 0; i < 8; i++) acc += a[i] + b[i];
+  for (int i = 0; i < 8; i++) acc += a[i];
   if (acc == 0x1234567812345678ULL) out[0] = acc;  // keep the chains alive
 }

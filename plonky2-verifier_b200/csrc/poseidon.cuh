@@ -1,129 +1,161 @@
 // Width-12 Poseidon permutation over Goldilocks, one thread per state, state in registers.
 //
-// Computes exactly `permutation` of the reference (src/Hash/Poseidon.hs:42-101: 4 full + 22
-// partial + 4 full rounds, x^7 s-box, MDS = circ(17,15,41,16,2,28,13,13,39,18,34,20)+diag(8,0..)),
-// but in Plonky2's fast-partial-round schedule, the same one the reference's PoseidonGate uses
-// (src/Gate/Custom/Poseidon.hs:92-100,125-137; tables src/Hash/Constants.hs:27-113).  The two
-// schedules are equal as functions (asserted by tests/test_oracle.py on the CPU and by the GPU
-// parity tests against the dense-MDS oracle).
+// Computes exactly `permutation` of the reference (src/Hash/Poseidon.hs:42-101): 30 rounds
+// (4 full + 22 partial + 4 full), each = add round constants, x^7 s-box (all 12 lanes in a full
+// round, lane 0 in a partial round), then the dense MDS layer
+//   M[i][j] = circ[(j-i) mod 12] + (i==j ? diag[i] : 0),  circ = (17,15,41,16,2,28,13,13,39,18,34,20), diag = (8,0,...)
+// (mdsMatrixCoeff, src/Hash/Constants.hs:21-25; linearDiffusion, Hash/Poseidon.hs:100-101).
 //
-// Cost model: 8 full rounds x (12 s-boxes x 4 mulmods + 288 small IMADs)
-// + 11x11 pre-matrix + 22 partial rounds x (1 s-box + 2x11 wide MACs).  Round constants are
-// folded into the accumulators of the preceding linear layer.
+// Why the DENSE layer in every round and not Plonky2's fast-partial-round tables, and why 22-bit
+// limbs: measured on B200 (p2v_int_pipe_peak), IMAD.WIDE.U32 issues every 4 cycles per SM
+// sub-partition, a 32-bit IMAD every 2 (like an ALU op).  A 64x64 mulmod needs 4 IMAD.WIDE + ~16
+// other instructions, so the 22 mulmods per round of the "fast" partial form cost far more FMA-pipe
+// time than a dense layer made of plain 32-bit IMADs: the state is cut into 22/22/20-bit limbs,
+// each limb column is accumulated with `IMAD acc = limb*coeff + acc` (row sum 264 keeps every
+// accumulator below 2^31: no carries, no IMAD.WIDE), and the three accumulators of an output are
+// recombined with one reduction.  ptxas turns the x16 / x2 coefficients into LEA on the ALU pipe by
+// itself, which balances the two pipes.  The fast-partial tables are still used by the
+// PoseidonGate constraint program (constraints.cuh), as in the reference.
+//
+// Round constants are folded into the accumulators of the preceding linear layer.
 #pragma once
 #include "gl.cuh"
 #include "poseidon_constants.h"
 
-// Round constants of the 8 full rounds, pre-split for use as IMAD.WIDE addends:
-//   c_full_rc[r][i][0] = lo32(rc), [1] = hi32(rc)      (r = 0..3 initial, 4..7 final = rounds 26..29)
-// plus the fast-partial tables.
+#ifndef POSEIDON_SBOX_GROUP
+#define POSEIDON_SBOX_GROUP 4 /* s-boxes per rotating-loop iteration in a full round: 4 or 12 */
+#endif
+
 struct PoseidonTables {
-  u64 rc[30][12];       // all_ROUND_CONSTANTS
-  u64 first_rc[12];     // fast_PARTIAL_FIRST_ROUND_CONSTANT
-  u64 partial_rc[22];   // fast_PARTIAL_ROUND_CONSTANTS
-  u64 vs[22][11];       // fast_PARTIAL_ROUND_VS
-  u64 w_hats[22][11];   // fast_PARTIAL_ROUND_W_HATS
-  u64 init_mat[11][11]; // fast_PARTIAL_ROUND_INITIAL_MATRIX, row-major as in the source
+  u64 rc[30][12];        // all_ROUND_CONSTANTS
+  u64 first_rc[12];      // fast_PARTIAL_FIRST_ROUND_CONSTANT   } used by the PoseidonGate
+  u64 partial_rc[22];    // fast_PARTIAL_ROUND_CONSTANTS        } constraint program only
+  u64 vs[22][11];        // fast_PARTIAL_ROUND_VS
+  u64 w_hats[22][11];    // fast_PARTIAL_ROUND_W_HATS
+  u64 init_mat[11][11];  // fast_PARTIAL_ROUND_INITIAL_MATRIX, row-major as in the source
 };
 
 static __constant__ PoseidonTables c_pt = {
     P2V_ALL_ROUND_CONSTANTS, P2V_FAST_PARTIAL_FIRST_RC, P2V_FAST_PARTIAL_RCS,
     P2V_FAST_PARTIAL_VS,     P2V_FAST_PARTIAL_W_HATS,   P2V_FAST_PARTIAL_INIT_MAT};
 
+// Round constants cut into 22/22/20-bit limbs (accumulator seeds of the linear layer); row r holds
+// the constants ADDED AFTER the linear layer of round r-1, i.e. rc[r]; row 30 is zero.
+struct PoseidonRcLimbs {
+  u32 v[31][12][4];
+};
+constexpr PoseidonRcLimbs poseidon_make_rc_limbs() {
+  constexpr u64 rc[360] = P2V_ALL_ROUND_CONSTANTS;
+  PoseidonRcLimbs t{};
+  for (int r = 0; r < 30; r++)
+    for (int i = 0; i < 12; i++) {
+      t.v[r][i][0] = (u32)(rc[r * 12 + i] & 0x3FFFFFULL);
+      t.v[r][i][1] = (u32)((rc[r * 12 + i] >> 22) & 0x3FFFFFULL);
+      t.v[r][i][2] = (u32)(rc[r * 12 + i] >> 44);
+    }
+  return t;
+}
+static __constant__ PoseidonRcLimbs c_rc3 = poseidon_make_rc_limbs();
+
 #define POSEIDON_MDS_ROW                                              \
   { 17u, 15u, 41u, 16u, 2u, 28u, 13u, 13u, 39u, 18u, 34u, 20u }
 
+// 128-bit (w3:w2:w1:w0) -> lazy 64-bit, carry-chain form (13 integer ops, no compares/selects).
+// NOTE on flags: `subc m,0,0` right after a SUB chain yields the borrow mask, but after an ADD chain
+// ptxas feeds the raw hardware carry into it (inverted meaning), so carries are materialised with
+// addc + neg instead.
+//   t = (w1:w0) - w3, minus EPS on borrow;  u = w2*(2^32-1) = (w2<<32) - w2;  r = t + u, plus EPS on carry.
+__device__ __forceinline__ u64 gl_reduce128_cc(u64 lo, u64 hi) {
+  u32 w0 = (u32)lo, w1 = (u32)(lo >> 32), w2 = (u32)hi, w3 = (u32)(hi >> 32), r0, r1;
+  asm("{\n\t.reg .u32 m,t0,t1,u0,u1;\n\t"
+      "sub.cc.u32 t0,%2,%5;\n\tsubc.cc.u32 t1,%3,0;\n\tsubc.u32 m,0,0;\n\t"
+      "sub.cc.u32 t0,t0,m;\n\tsubc.u32 t1,t1,0;\n\t"
+      "sub.cc.u32 u0,0,%4;\n\tsubc.u32 u1,%4,0;\n\t"
+      "add.cc.u32 t0,t0,u0;\n\taddc.cc.u32 t1,t1,u1;\n\taddc.u32 m,0,0;\n\tneg.s32 m,m;\n\t"
+      "add.cc.u32 %0,t0,m;\n\taddc.u32 %1,t1,0;\n\t}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(w0), "r"(w1), "r"(w2), "r"(w3));
+  return ((u64)r1 << 32) | r0;
+}
+__device__ __forceinline__ u64 gl_mul_cc(u64 a, u64 b) {
+  // one 128-bit product: ptxas shares the partial products between the low and the high half
+  unsigned __int128 m = (unsigned __int128)a * b;
+  return gl_reduce128_cc((u64)m, (u64)(m >> 64));
+}
+
 // x^7 with 2 squarings + 2 multiplications (sbox1, Hash/Poseidon.hs:79-80)
 __device__ __forceinline__ u64 poseidon_sbox(u64 x) {
-  u64 x2 = gl_sqr(x);
-  u64 x3 = gl_mul(x, x2);
-  u64 x4 = gl_sqr(x2);
-  return gl_mul(x3, x4);
+  u64 x2 = gl_mul_cc(x, x);
+  u64 x3 = gl_mul_cc(x, x2);
+  u64 x4 = gl_mul_cc(x2, x2);
+  return gl_mul_cc(x3, x4);
 }
 
-// out_i = add_i + sum_j M[i][j] * s_j  with M[i][j] = circ[(j-i) mod 12] + (i==j ? diag[i] : 0)
-// (mdsMatrixCoeff, Hash/Constants.hs:24-25).  The state is split into 32-bit halves; each half is
-// accumulated in a u64 (row sum <= 264, so < 2^41: no carries), then recombined with one
-// reduction per output.  `addlo/addhi` carry the next round's constants.
-__device__ __forceinline__ void poseidon_mds(u64 (&s)[12], const u64 *__restrict__ add) {
+// s <- rc_next + MDS * s on 22/22/20-bit limbs.  Bounds: limb < 2^22, row sum of the coefficients
+// <= 264, seed < 2^22  =>  every accumulator < 2^31.
+template <int I, int J>
+__device__ __forceinline__ void poseidon_mds_acc(u32 &a0, u32 &a1, u32 &a2, const u32 (&l0)[12], const u32 (&l1)[12], const u32 (&l2)[12]) {
   constexpr u32 C[12] = POSEIDON_MDS_ROW;
-  u32 lo[12], hi[12];
+  constexpr u32 c = C[(J - I + 12) % 12] + ((I == 0 && J == 0) ? 8u : 0u);
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a0) : "r"(l0[J]), "n"(c));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a1) : "r"(l1[J]), "n"(c));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a2) : "r"(l2[J]), "n"(c));
+  if constexpr (J + 1 < 12) poseidon_mds_acc<I, J + 1>(a0, a1, a2, l0, l1, l2);
+}
+template <int I>
+__device__ __forceinline__ void poseidon_mds_row(u64 (&s)[12], const u32 (&l0)[12], const u32 (&l1)[12], const u32 (&l2)[12], int next_round) {
+  u32 a0 = c_rc3.v[next_round][I][0], a1 = c_rc3.v[next_round][I][1], a2 = c_rc3.v[next_round][I][2];
+  poseidon_mds_acc<I, 0>(a0, a1, a2, l0, l1, l2);
+  // V = a0 + a1*2^22 + a2*2^44 (< 2^74) as words w0,w1,w2 (w2 < 2^10), then
+  // (w1:w0) + w2*2^64 == (w1 + w2 : w0) - w2 (mod p); a wrap of w1 + w2 adds another 2^64 == 2^32 - 1.
+  // The final subtraction cannot borrow out: its high word is >= 1 whenever w2 > 0.
+  u32 r0, r1;
+  asm("{\n\t.reg .u32 t,u,w2,c;\n\t"
+      "shl.b32 t,%3,22;\n\tadd.cc.u32 %0,%2,t;\n\t"
+      "shr.u32 t,%3,10;\n\tshl.b32 u,%4,12;\n\taddc.cc.u32 %1,t,u;\n\t"
+      "shr.u32 w2,%4,20;\n\taddc.u32 w2,w2,0;\n\t"
+      "add.cc.u32 %1,%1,w2;\n\taddc.u32 c,0,0;\n\t"
+      "add.u32 w2,w2,c;\n\tadd.u32 %1,%1,c;\n\t"
+      "sub.cc.u32 %0,%0,w2;\n\tsubc.u32 %1,%1,0;\n\t}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"(a0), "r"(a1), "r"(a2));
+  s[I] = ((u64)r1 << 32) | r0;
+  if constexpr (I + 1 < 12) poseidon_mds_row<I + 1>(s, l0, l1, l2, next_round);
+}
+__device__ __forceinline__ void poseidon_mds(u64 (&s)[12], int next_round) {
+  u32 l0[12], l1[12], l2[12];
 #pragma unroll
   for (int j = 0; j < 12; j++) {
-    lo[j] = (u32)s[j];
-    hi[j] = (u32)(s[j] >> 32);
+    u32 xl = (u32)s[j], xh = (u32)(s[j] >> 32);
+    l0[j] = xl & 0x3FFFFFu;
+    l1[j] = __funnelshift_r(xl, xh, 22) & 0x3FFFFFu;
+    l2[j] = xh >> 12;
   }
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    u64 a = add ? add[i] : 0;
-    u64 L = (u32)a, H = (u32)(a >> 32);
-#pragma unroll
-    for (int j = 0; j < 12; j++) {
-      u32 c = C[(j - i + 12) % 12] + ((i == 0 && j == 0) ? 8u : 0u);
-      L += (u64)lo[j] * c;
-      H += (u64)hi[j] * c;
-    }
-    // value = L + 2^32*H,  H = Hh*2^32 + Hl  ->  L + Hh*(2^32-1) + (Hl << 32)
-    u32 Hl = (u32)H, Hh = (u32)(H >> 32);
-    u64 A = L + (u64)Hh * 0xFFFFFFFFu;  // < 2^42
-    u64 r = A + ((u64)Hl << 32);
-    if (r < A) r += GL_EPS;  // wrapped r < 2^42: no second wrap
-    s[i] = r;
-  }
-}
-
-__device__ __forceinline__ void poseidon_full_round(u64 (&s)[12], const u64 *__restrict__ next_rc) {
-#pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(s[i]);
-  poseidon_mds(s, next_rc);
+  poseidon_mds_row<0>(s, l0, l1, l2, next_round);
 }
 
 // The permutation.  Input: lazy u64 (any values); output: lazy u64 (apply gl_canon before use as data).
 __device__ __forceinline__ void poseidon_permute(u64 (&s)[12]) {
-  // round 0 constants
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], c_pt.rc[0][i]);
-  // initial full rounds 0..3; rounds 0..2 fold in the next round's constants, round 3 folds in
-  // FAST_PARTIAL_FIRST_ROUND_CONSTANT.
 #pragma unroll 1
-  for (int r = 0; r < 4; r++) poseidon_full_round(s, r < 3 ? c_pt.rc[r + 1] : c_pt.first_rc);
-  // pre-partial matrix: s[1..] <- INITIAL_MATRIX^T-style product (mdsInitPartial,
-  // Gate/Custom/Poseidon.hs:121-125: out_i = sum_j INITIAL_MATRIX[j][i] * s_{j+1})
-  {
-    // register-rotating loop over the input lane j: acc_i += INITIAL_MATRIX[j][i] * s_{j+1};
-    // all register indices stay static so nothing falls into local memory.
-    u64 acc[11];
-#pragma unroll
-    for (int i = 0; i < 11; i++) acc[i] = 0;
+  for (int r = 0; r < 30; r++) {
+    if (r < 4 || r >= 26) {
+      // full round: 12 s-boxes, as a register-rotating loop so that the body stays small for the
+      // instruction cache while every register index remains static
 #pragma unroll 1
-    for (int j = 0; j < 11; j++) {
-      u64 x = s[1];
+      for (int g = 0; g < 12 / POSEIDON_SBOX_GROUP; g++) {
+        u64 t[POSEIDON_SBOX_GROUP];
 #pragma unroll
-      for (int i = 1; i < 11; i++) s[i] = s[i + 1];
-      s[11] = x;
+        for (int k = 0; k < POSEIDON_SBOX_GROUP; k++) t[k] = poseidon_sbox(s[k]);
 #pragma unroll
-      for (int i = 0; i < 11; i++) acc[i] = gl_add(acc[i], gl_mul(c_pt.init_mat[j][i], x));
+        for (int k = 0; k + POSEIDON_SBOX_GROUP < 12; k++) s[k] = s[k + POSEIDON_SBOX_GROUP];
+#pragma unroll
+        for (int k = 0; k < POSEIDON_SBOX_GROUP; k++) s[12 - POSEIDON_SBOX_GROUP + k] = t[k];
+      }
+    } else {
+      s[0] = poseidon_sbox(s[0]);
     }
-#pragma unroll
-    for (int i = 0; i < 11; i++) s[i + 1] = acc[i];
+    poseidon_mds(s, r + 1);
   }
-  // 22 partial rounds
-#pragma unroll 1
-  for (int r = 0; r < 22; r++) {
-    u64 y = poseidon_sbox(s[0]);
-    y = gl_add(y, c_pt.partial_rc[r]);  // entry 21 is 0
-    // d = 25*y + sum s_{i+1} * W_HAT[r][i];   s_{i+1} += y * VS[r][i]
-    u64 d = gl_mul_small(y, 25u);
-#pragma unroll
-    for (int i = 0; i < 11; i++) {
-      d = gl_add(d, gl_mul(s[i + 1], c_pt.w_hats[r][i]));
-      s[i + 1] = gl_add(s[i + 1], gl_mul(y, c_pt.vs[r][i]));
-    }
-    s[0] = d;
-  }
-  // final full rounds 26..29
-#pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], c_pt.rc[26][i]);
-#pragma unroll 1
-  for (int r = 0; r < 4; r++) poseidon_full_round(s, r < 3 ? c_pt.rc[27 + r] : nullptr);
 }

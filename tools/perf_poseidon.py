@@ -7,7 +7,7 @@ import plonky2_verifier_b200 as p2v
 
 ctx = p2v.Context(0)
 peaks = {m: ctx.int_pipe_peak(m) for m in range(5)}
-print("int-pipe peaks (thread-ops/s): imad.wide %.3e imad %.3e iadd3 %.3e lop3 %.3e wide+iadd %.3e" % tuple(peaks[m] for m in range(5)))
+print("int-pipe groups/s: lop3+imad.wide %.3e | 2lop3+imad.wide %.3e | lop3+imad32 %.3e | lop3+iadd3 %.3e | 2imad.wide+lop3 %.3e" % tuple(peaks[m] for m in range(5)))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 2048 * 8
 x = torch.randint(0, 2**62, (12, n), dtype=torch.int64, device="cuda")
 y = torch.empty_like(x)
