@@ -134,11 +134,12 @@ size_t carve(const DevCircuit &d, size_t m, char *base, Workspace *ws, bool want
   u64 *pre = (u64 *)take(4 * m * 8);
   u64 *comb = (u64 *)take((size_t)2 * d.r * m * 8);
   u32 *qstat = (u32 *)take((size_t)d.Q * m * 4);
+  uint8_t *tree_ok = (uint8_t *)take((size_t)(4 + d.nsteps) * d.Q * m);
   u64 *folded = want_folded ? (u64 *)take((size_t)2 * d.Q * m * 8) : nullptr;
   uint8_t *eq = (uint8_t *)take(m);
   if (ws) {
     ws->pp = pp; ws->qp = qp; ws->ch = ch; ws->pih = pih; ws->pre = pre; ws->comb = comb; ws->qstat = qstat;
-    ws->folded = folded; ws->eqmask = eq;
+    ws->folded = folded; ws->eqmask = eq; ws->tree_ok = tree_ok;
   }
   return off;
 }
@@ -298,7 +299,11 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     if (what & RUN_CONSTRAINTS) P2V_LAUNCH(ctx, k_constraints, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
     P2V_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     // K6
-    if (what & RUN_FRI) P2V_LAUNCH(ctx, k_fri_query, p2v_grid_for(ctx, m * d.Q, 256, 2), 256, 0, d, ws, m);
+    if (what & RUN_FRI) {
+      P2V_LAUNCH(ctx, k_fri_merkle, p2v_grid_for(ctx, m * d.Q * (4 + d.nsteps), 256, 3), 256, 0, d, ws, m);
+      P2V_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+      P2V_LAUNCH(ctx, k_fri_query, p2v_grid_for(ctx, m * d.Q, 256, 4), 256, 0, d, ws, m);
+    }
     P2V_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     // K7
     if (out.verdict_mode) {
@@ -339,6 +344,11 @@ static int resolveTimings(p2v_ctx *ctx) {
     float ms = 0;
     P2V_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
     ctx->last_ms[names[i]] = ms;
+  }
+  {  // "fri" = k_fri_merkle + k_fri_query; the Merkle part separately (only valid if FRI ran)
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[6]) == cudaSuccess) ctx->last_ms["fri_merkle"] = ms;
+    else cudaGetLastError();
   }
   return P2V_OK;
 }

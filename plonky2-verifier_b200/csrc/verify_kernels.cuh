@@ -58,6 +58,7 @@ struct Workspace {
   u64 *pre;    // [4][n]          precomputed reduced openings Y0, Y1 (Plonk/FRI.hs:128-134)
   u64 *comb;   // [2r][n]         combined constraints
   u32 *qstat;  // [Q][n]          per-query status
+  uint8_t *tree_ok;  // [4+nsteps][Q][n]  Merkle opening verdicts (K6a -> K6b)
   u64 *folded; // [2][Q*n]        final folded evaluation per query (debug/parity output)
   uint8_t *eqmask;  // [n]        bit j: round j of the quotient identity holds
 };
@@ -239,12 +240,85 @@ __global__ void __launch_bounds__(128) k_challenges(const __grid_constant__ DevC
   }
 }
 
-// ---- K6: one FRI query round per thread (checkQueryRound, Plonk/FRI.hs:380-407) ------------------
-// Thread t = (q, proof).  Phase 1: the 4 initial-tree openings and the nsteps coset openings are
-// Merkle-checked through a single permutation call site.  Phase 2: combineInitial, coset folding
-// and the final-polynomial check.  The status keeps the FIRST failure in reference order
-// (SURVEY.md App. E): INIT_MERKLE, then per step STEP_MERKLE, STEP_EVAL, finally FALSE_FINAL.
-__global__ void __launch_bounds__(256, 2) k_fri_query(const __grid_constant__ DevCircuit c, Workspace ws, size_t n) {
+// ---- K6a: Merkle openings of the FRI query rounds (checkInitialTreeProofs Plonk/FRI.hs:105-117,
+// the proofCheckOK of foldingStep :316) -----------------------------------------------------------
+// Thread t = (tree, q, proof), tree-major so that a warp works on one tree: trees 0..3 are the
+// initial oracles (leaf = row of the oracle, path to the cap), trees 4.. are the commit-phase
+// trees (leaf = flattened coset evals).  ~97% of all permutations of a verification run here,
+// through a single permutation call site.
+__global__ void __launch_bounds__(256, 3) k_fri_merkle(const __grid_constant__ DevCircuit c, Workspace ws, size_t n) {
+  const int Q = c.Q;
+  const size_t per_tree = n * (size_t)Q;
+  const size_t total = per_tree * (size_t)(4 + c.nsteps);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const u64 *__restrict__ pp = ws.pp;
+  const u64 *__restrict__ qp = ws.qp;
+  const p2v_layout &L = c.L;
+  const size_t qstride = per_tree;  // word w of (q, proof) at qp[w*Q*n + q*n + proof]
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    int tr = (int)(t / per_tree);
+    size_t rem = t - (size_t)tr * per_tree;  // = q*n + proof
+    int q = (int)(rem / n);
+    size_t p = rem - (size_t)q * n;
+    const u64 *__restrict__ qbase = qp + rem;
+    u32 index = (u32)ws.ch[(size_t)(c.ch_idx + q) * n + p];
+    int leaf_off, width, sib_off, plen, cap_off;
+    if (tr < 4) {
+      leaf_off = L.q_off_leaf[tr]; width = L.oracle_width[tr]; sib_off = L.q_off_sibs[tr]; plen = L.init_path_len;
+      cap_off = tr == 1 ? L.off_wires_cap : tr == 2 ? L.off_zs_pp_cap : L.off_quotient_cap;
+    } else {
+      int st = tr - 4;
+      leaf_off = L.q_off_step_evals[st]; width = 2 << c.arity_bits[st]; sib_off = L.q_off_step_sibs[st]; plen = L.step_path_len[st];
+      index >>= c.cum_bits[st + 1];  // query_index_rev newQueryIdx
+      cap_off = L.off_commit_caps + st * L.cap_words;
+    }
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    int nblk = (width + 7) >> 3;
+    int iters = nblk + plen;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+      if (it < nblk) {
+        // sponge block, Hash/Sponge.hs:26-31 (overwrite the first k lanes)
+        int k = width - it * 8;
+        const u64 *src = qbase + (size_t)(leaf_off + it * 8) * qstride;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (i < k) s[i] = src[(size_t)i * qstride];
+      } else {
+        // compress with the sibling, Hash/Merkle.hs:30-37
+        const u64 *src = qbase + (size_t)(sib_off + (it - nblk) * 4) * qstride;
+        bool even = (index & 1u) == 0;
+        index >>= 1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          u64 sib = src[(size_t)i * qstride];
+          u64 node = s[i];
+          s[i] = even ? node : sib;
+          s[4 + i] = even ? sib : node;
+          s[8 + i] = 0;
+        }
+      }
+      poseidon_permute(s);
+    }
+    // compare with cap[index] (Merkle.hs:39-42); cap 0 is the verifier key, the others come with the proof
+    bool ok = index < (1u << c.cap_height);
+    u32 ci = ok ? index : 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      u64 want = tr == 0 ? __ldg(c.vkey + ci * 4 + i) : pp[(size_t)(cap_off + ci * 4 + i) * n + p];
+      ok = ok && (gl_canon(s[i]) == gl_canon(want));
+    }
+    ws.tree_ok[t] = ok ? 1 : 0;
+  }
+}
+
+// ---- K6b: the arithmetic of a query round (checkQueryRound, Plonk/FRI.hs:380-407): combineInitial,
+// coset folding, final-polynomial check; merges the Merkle verdicts of K6a into the per-query
+// status, keeping the FIRST failure in reference order: INIT_MERKLE, then per
+// step STEP_MERKLE, STEP_EVAL, finally FALSE_FINAL.  Thread t = (q, proof).
+__global__ void __launch_bounds__(256) k_fri_query(const __grid_constant__ DevCircuit c, Workspace ws, size_t n) {
   size_t total = n * (size_t)c.Q;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   const u64 *__restrict__ pp = ws.pp;
@@ -257,67 +331,10 @@ __global__ void __launch_bounds__(256, 2) k_fri_query(const __grid_constant__ De
     const u64 *__restrict__ qbase = qp + (size_t)q * n + p;  // word w of this query at qbase[w*Q*n]
     const size_t qstride = (size_t)Q * n;
     u32 idx = (u32)ws.ch[(size_t)(c.ch_idx + q) * n + p];
-
-    // ---------------- phase 1: Merkle openings ----------------
-    u32 init_bad = 0;   // mask of failing initial oracles
-    u32 step_bad = 0;   // mask of failing step trees
-    int ntrees = 4 + c.nsteps;
+    u32 init_bad = 0, step_bad = 0;
 #pragma unroll 1
-    for (int tr = 0; tr < ntrees; tr++) {
-      int leaf_off, width, sib_off, plen;
-      u32 index;
-      if (tr < 4) {
-        leaf_off = L.q_off_leaf[tr]; width = L.oracle_width[tr]; sib_off = L.q_off_sibs[tr]; plen = L.init_path_len;
-        index = idx;
-      } else {
-        int st = tr - 4;
-        leaf_off = L.q_off_step_evals[st]; width = 2 << c.arity_bits[st]; sib_off = L.q_off_step_sibs[st]; plen = L.step_path_len[st];
-        index = idx >> c.cum_bits[st + 1];  // query_index_rev newQueryIdx, Plonk/FRI.hs:316
-      }
-      u64 s[12];
-#pragma unroll
-      for (int i = 0; i < 12; i++) s[i] = 0;
-      int nblk = (width + 7) >> 3;
-      int iters = nblk + plen;
-#pragma unroll 1
-      for (int it = 0; it < iters; it++) {
-        if (it < nblk) {
-          // sponge block, Hash/Sponge.hs:26-31 (overwrite the first k lanes)
-          int k = width - it * 8;
-          const u64 *src = qbase + (size_t)(leaf_off + it * 8) * qstride;
-#pragma unroll
-          for (int i = 0; i < 8; i++)
-            if (i < k) s[i] = src[(size_t)i * qstride];
-        } else {
-          // compress with the sibling, Hash/Merkle.hs:30-37
-          const u64 *src = qbase + (size_t)(sib_off + (it - nblk) * 4) * qstride;
-          bool even = (index & 1u) == 0;
-          index >>= 1;
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            u64 sib = src[(size_t)i * qstride];
-            u64 node = s[i];
-            s[i] = even ? node : sib;
-            s[4 + i] = even ? sib : node;
-            s[8 + i] = 0;
-          }
-        }
-        poseidon_permute(s);
-      }
-      // compare with cap[index] (Merkle.hs:39-42); cap 0 is the verifier key, the others come with the proof
-      bool ok = index < (1u << c.cap_height);
-      u32 ci = ok ? index : 0;
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        u64 want;
-        if (tr == 0) want = __ldg(c.vkey + ci * 4 + i);
-        else {
-          int cap_off = tr == 1 ? L.off_wires_cap : tr == 2 ? L.off_zs_pp_cap : tr == 3 ? L.off_quotient_cap : L.off_commit_caps + (tr - 4) * L.cap_words;
-          want = pp[(size_t)(cap_off + ci * 4 + i) * n + p];
-        }
-        ok = ok && (gl_canon(s[i]) == gl_canon(want));
-      }
-      if (!ok) {
+    for (int tr = 0; tr < 4 + c.nsteps; tr++) {
+      if (!ws.tree_ok[(size_t)tr * total + t]) {
         if (tr < 4) init_bad |= 1u << tr;
         else step_bad |= 1u << (tr - 4);
       }
