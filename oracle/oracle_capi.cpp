@@ -174,6 +174,49 @@ int orc_gate_constraints(const p2v_shape *shape, int gate_index, const uint64_t 
   }
 }
 
+// ---- small algebra / transcript probes for the known-answer tests -----------------
+// op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 a^b (b as a signed 64-bit exponent), 5 subgroupGenerator(a), 6 div
+uint64_t orc_field_op(int op, uint64_t a, uint64_t b) {
+  switch (op) {
+    case 0: return (F(a) * F(b)).v;
+    case 1: return (F(a) + F(b)).v;
+    case 2: return (F(a) - F(b)).v;
+    case 3: return inv(F(a)).v;
+    case 4: return powi(F(a), (long long)b).v;
+    case 5: return subgroupGenerator((int)a).v;
+    case 6: return (F(a) / F(b)).v;
+  }
+  return 0;
+}
+// op: 0 mul, 1 inv(x), 2 div, 3 x^e (e in y[0], signed)
+void orc_ext_op(int op, const uint64_t *x, const uint64_t *y, uint64_t *out) {
+  FExt a = FExt(F(x[0]), F(x[1]));
+  FExt b = y ? FExt(F(y[0]), F(y[1])) : FExt();
+  FExt r;
+  switch (op) {
+    case 0: r = a * b; break;
+    case 1: r = invExt(a); break;
+    case 2: r = a / b; break;
+    default: r = powExtI(a, (long long)y[0]); break;
+  }
+  out[0] = r.r.v; out[1] = r.i.v;
+}
+// Duplex script (Challenge/Pure.hs): ops[i] >= 0 absorbs that many of the next inputs, ops[i] < 0 squeezes
+// -ops[i] field elements; returns the number of squeezed outputs.
+int orc_duplex_script(const int *ops, int nops, const uint64_t *inputs, uint64_t *outputs, unsigned long long *perms) {
+  Duplex dx(zeroState());
+  permCounter() = 0;
+  int in = 0, out = 0;
+  for (int i = 0; i < nops; i++) {
+    if (ops[i] >= 0) for (int k = 0; k < ops[i]; k++) dx.absorb(F(inputs[in++]));
+    else for (int k = 0; k < -ops[i]; k++) outputs[out++] = dx.squeezeFelt().v;
+  }
+  if (perms) *perms = permCounter();
+  return out;
+}
+// reverseBitsInt / evalLagrange0 / foldCosetWith probes
+uint64_t orc_reverse_bits(int n, uint64_t w) { return reverseBits(n, w); }
+
 // layout implied by a shape, computed by the oracle's own reader/writer (for comparison with p2v_shape_layout)
 size_t orc_blob_words(const p2v_shape *shape, const uint64_t *blob) {
   CommonCircuitData c = commonFromShape(*shape);

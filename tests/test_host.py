@@ -1,0 +1,229 @@
+"""CPU tests of the product's host side (no GPU): the C-ABI library loads and exports every symbol that
+include/p2v.h declares; the JSON / gate-string parsers agree with an independent Python reading of the same
+files (json module = exact integers); shape errors are reported, not crashed on; without a GPU the context
+refuses to start (there is no CPU fallback)."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fixtures
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = 0xFFFFFFFF00000001
+
+
+def test_library_exports_every_declared_symbol(p2v):
+    hdr = open(os.path.join(ROOT, "include", "p2v.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(p2v_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = C.CDLL(p2v.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), "libp2v.so does not export %s" % sym
+    assert declared == set(p2v.EXPORTED_SYMBOLS)
+    assert p2v.lib().p2v_abi_version() == 1
+
+
+def test_no_cpu_fallback(p2v):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(p2v.P2VError) as e:
+        p2v.Context(0)
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+
+
+# ---- independent Python reading of the wire format ----------------------------------
+
+def py_blob(common, proof_json):
+    """Flatten a *_proof.json in the field order of Types.hs:251-279 (the p2v_layout order)."""
+    out = []
+    f = lambda x: out.append(int(x) % P)
+    dig = lambda d: [f(x) for x in d["elements"]]
+    cap = lambda c: [dig(d) for d in c]
+    ext = lambda xs: [(f(a), f(b)) for a, b in xs]
+    pr = proof_json["proof"]
+    cap(pr["wires_cap"]); cap(pr["plonk_zs_partial_products_cap"]); cap(pr["quotient_polys_cap"])
+    op = pr["openings"]
+    for k in ("constants", "plonk_sigmas", "wires", "plonk_zs", "plonk_zs_next", "partial_products", "quotient_polys",
+              "lookup_zs", "lookup_zs_next"):
+        ext(op[k])
+    fri = pr["opening_proof"]
+    for c in fri["commit_phase_merkle_caps"]:
+        cap(c)
+    ext(fri["final_poly"]["coeffs"])
+    f(fri["pow_witness"])
+    for x in proof_json["public_inputs"]:
+        f(x)
+    for rd in fri["query_round_proofs"]:
+        for leaf, path in rd["initial_trees_proof"]["evals_proofs"]:
+            for x in leaf:
+                f(x)
+            cap(path["siblings"])
+        for st in rd["steps"]:
+            ext(st["evals"])
+            cap(st["merkle_proof"]["siblings"])
+    return np.array(out, dtype=np.uint64)
+
+
+GATE_RE = [
+    (r"^ArithmeticGate \{ num_ops: (\d+) \}$", 0), (r"^ArithmeticExtensionGate \{ num_ops: (\d+) \}$", 1),
+    (r"^BaseSumGate \{ num_limbs: (\d+) \} \+ Base: (\d+)$", 2),
+    (r"^CosetInterpolationGate \{ subgroup_bits: (\d+), degree: (\d+), barycentric_weights: \[([0-9, ]*)\], _phantom: .*\}<D=2>$", 3),
+    (r"^ConstantGate \{ num_consts: (\d+) \}", 4), (r"^ExponentiationGate \{ num_power_bits: (\d+) \}", 5),
+    (r"^LookupGate \{ num_slots: (\d+), lut_hash: \[[0-9, ]*\] \}", 6),
+    (r"^LookupTableGate \{ num_slots: (\d+), lut_hash: \[[0-9, ]*\], last_lut_row: (\d+) \}", 7),
+    (r"^MulExtensionGate \{ num_ops: (\d+) \}", 8), (r"^NoopGate", 9), (r"^PublicInputGate", 10),
+    (r"^PoseidonGate\(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>\)<WIDTH=(\d+)>$", 11),
+    (r"^PoseidonMdsGate\(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>\)<WIDTH=(\d+)>$", 12),
+    (r"^RandomAccessGate \{ bits: (\d+), num_copies: (\d+), num_extra_constants: (\d+), _phantom: .*\}<D=2>", 13),
+    (r"^ReducingGate \{ num_coeffs: (\d+) \}", 14), (r"^ReducingExtensionGate \{ num_coeffs: (\d+) \}", 15),
+]
+
+
+def py_gate(s):
+    for rx, kind in GATE_RE:
+        m = re.match(rx, s)
+        if m:
+            g = [x for x in m.groups()]
+            if kind == 3:
+                return kind, [int(g[0]), int(g[1])], [int(x) % P for x in g[2].split(",") if x.strip()]
+            return kind, [int(x) for x in g], []
+    return 16, [], []
+
+
+@pytest.mark.parametrize("name", fixtures.ACCEPTING)
+def test_parsers_match_python_reading(p2v, name):
+    common = json.loads(fixtures.read(name, "common"))
+    shape, lay, vkey, blob = fixtures.load(name)
+    cfg, fc = common["config"], common["config"]["fri_config"]
+    assert (shape.num_wires, shape.num_routed_wires, shape.num_gate_constants, shape.num_challenges) == (
+        cfg["num_wires"], cfg["num_routed_wires"], cfg["num_constants"], cfg["num_challenges"])
+    assert (shape.rate_bits, shape.cap_height, shape.pow_bits, shape.num_queries) == (
+        fc["rate_bits"], fc["cap_height"], fc["proof_of_work_bits"], fc["num_query_rounds"])
+    assert shape.degree_bits == common["fri_params"]["degree_bits"]
+    # expandReductionStrategy, Plonk/FRI.hs:337-354
+    strat = fc["reduction_strategy"]
+    if "ConstantArityBits" in strat:
+        a, fbits = strat["ConstantArityBits"]
+        steps, logn = [], shape.degree_bits
+        while logn > fbits:
+            steps.append(a)
+            logn -= a
+    else:
+        steps = strat["Fixed"]
+    assert list(shape.step_arity_bits)[: shape.num_steps] == steps
+    assert shape.final_poly_len == 1 << (shape.degree_bits - sum(steps))
+    for k in ("quotient_degree_factor", "num_constants", "num_public_inputs", "num_partial_products", "num_lookup_polys",
+              "num_lookup_selectors"):
+        assert getattr(shape, k) == common[k], k
+    assert [int(x) for x in shape.k_is[: shape.num_routed_wires]] == [int(x) % P for x in common["k_is"]]
+    sel = common["selectors_info"]
+    assert [shape.gates[i].group for i in range(shape.num_gates)] == sel["selector_indices"]
+    assert [(shape.group_start[i], shape.group_end[i]) for i in range(shape.num_groups)] == [(g["start"], g["end"]) for g in sel["groups"]]
+    assert shape.num_gates == len(common["gates"])
+    for i, s in enumerate(common["gates"]):
+        kind, params, weights = py_gate(s)
+        g = shape.gates[i]
+        assert g.kind == kind, s
+        assert [g.p0, g.p1, g.p2][: len(params)] == params, s
+        assert [int(x) for x in shape.weights[g.weights_off: g.weights_off + g.weights_len]] == weights
+    luts = common["luts"]
+    assert shape.num_luts == len(luts)
+    for k, t in enumerate(luts):
+        got = [(int(shape.lut_pairs[2 * j]), int(shape.lut_pairs[2 * j + 1])) for j in range(shape.lut_off[k], shape.lut_off[k + 1])]
+        assert got == [(a % P, b % P) for a, b in t]
+    # proof and vkey blobs
+    want = py_blob(common, json.loads(fixtures.read(name, "proof")))
+    assert lay.blob_words == len(want)
+    assert np.array_equal(blob, want)
+    vk = json.loads(fixtures.read(name, "vkey"))
+    want_vk = [int(x) % P for d in vk["constants_sigmas_cap"] for x in d["elements"]] + [int(x) % P for x in vk["circuit_digest"]["elements"]]
+    assert [int(x) for x in vkey] == want_vk
+
+
+def test_layout_offsets_are_consistent(p2v):
+    shape, lay, vkey, blob = fixtures.load("s12")
+    assert lay.blob_words == lay.proof_words + shape.num_queries * lay.query_words == 15881
+    assert list(lay.oracle_width) == [85, 135, 20, 16]  # commentary/FRI.md:256
+    assert lay.init_path_len == 11 and list(lay.step_path_len)[:2] == [7, 3]
+    assert p2v.challenges_words(shape) == 3 * 2 + 2 + 2 + 4 + 1 + 28
+
+
+GATE_CASES = [
+    ("ArithmeticGate { num_ops: 20 }", 0, [20], 20),
+    ("ArithmeticGate { num_ops: 20 } trailing", 16, [], 0),  # withEOF (Parser.hs:134-136)
+    ("ArithmeticExtensionGate { num_ops: 10 }", 1, [10], 20),
+    ("BaseSumGate { num_limbs: 63 } + Base: 2", 2, [63, 2], 64),
+    ("ConstantGate { num_consts: 2 }", 4, [2], 2),
+    ("ConstantGate { num_consts: 2 } and then some", 4, [2], 2),  # no EOF check in constantGateP (Parser.hs:165-167)
+    ("ConstantGate{num_consts:2}", 4, [2], 2),  # `spaces` accepts zero blanks
+    ("ExponentiationGate { num_power_bits: 66 }", 5, [66], 67),
+    ("MulExtensionGate { num_ops: 13 }", 8, [13], 26),
+    ("NoopGate", 9, [], 0), ("NoopGateWithSuffix", 9, [], 0),  # `string "NoopGate"` only
+    ("PublicInputGate", 10, [], 4),
+    ("PoseidonGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>", 11, [12], 123),
+    ("PoseidonMdsGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>", 12, [12], 24),
+    ("RandomAccessGate { bits: 4, num_copies: 4, num_extra_constants: 2, _phantom: PhantomData<plonky2_field::goldilocks_field::GoldilocksField> }<D=2>", 13, [4, 4, 2], 26),
+    ("ReducingGate { num_coeffs: 43 }", 14, [43], 86), ("ReducingGate { num_coeffs: 43 }<D=2>", 14, [43], 86),
+    ("ReducingExtensionGate { num_coeffs: 32 }", 15, [32], 64),
+    ("LookupGate { num_slots: 40, lut_hash: [1, 2, 3] }", 6, [40], 0),
+    ("LookupTableGate { num_slots: 26, lut_hash: [9, 8], last_lut_row: 3 }", 7, [26, 3], 0),
+    ("SomeFutureGate { x: 1 }", 16, [], 0), ("", 16, [], 0), ("arithmeticgate { num_ops: 1 }", 16, [], 0),
+]
+
+
+@pytest.mark.parametrize("text,kind,params,ncons", GATE_CASES)
+def test_gate_string_parser(p2v, text, kind, params, ncons):
+    g, w = p2v.parse_gate(text)
+    assert g.kind == kind
+    assert [g.p0, g.p1, g.p2][: len(params)] == params
+    assert g.num_constraints == ncons
+
+
+def test_coset_gate_string(p2v):
+    shape, *_ = fixtures.load("s12")
+    text = json.loads(fixtures.read("s12", "common"))["gates"][11]
+    g, w = p2v.parse_gate(text)
+    assert g.kind == 3 and (g.p0, g.p1) == (4, 6) and len(w) == 16 and g.num_constraints == 12
+    assert p2v.parse_gate(text.replace("<D=2>", ""))[0].kind == 16  # the suffix is mandatory (Parser.hs:162)
+
+
+def test_shape_and_parse_errors(p2v):
+    shape, lay, vkey, blob = fixtures.load("small6")
+    proof = json.loads(fixtures.read("small6", "proof"))
+    def expect(obj, code):
+        with pytest.raises(p2v.P2VError) as e:
+            p2v.parse_proof(json.dumps(obj), shape)
+        assert e.value.code == code, str(e.value)
+    bad = json.loads(json.dumps(proof)); bad["proof"]["wires_cap"].pop()
+    expect(bad, -5)  # validateMerkleCapLength (Plonk/FRI.hs:79-85)
+    bad = json.loads(json.dumps(proof)); bad["proof"]["opening_proof"]["query_round_proofs"].pop()
+    expect(bad, -5)  # safeZipWith (Plonk/FRI.hs:372)
+    bad = json.loads(json.dumps(proof)); bad["proof"]["opening_proof"]["query_round_proofs"][0]["initial_trees_proof"]["evals_proofs"].pop()
+    expect(bad, -5)  # expecting 4 Merkle proofs (Plonk/FRI.hs:107)
+    bad = json.loads(json.dumps(proof)); bad["proof"]["opening_proof"]["query_round_proofs"][1]["steps"][0]["evals"].pop()
+    expect(bad, -5)  # reduction strategy incompatibility (Plonk/FRI.hs:312)
+    bad = json.loads(json.dumps(proof)); bad["proof"]["openings"]["wires"][0][0] = 1.5
+    expect(bad, -4)
+    bad = json.loads(json.dumps(proof)); del bad["public_inputs"]
+    expect(bad, -4)
+    with pytest.raises(p2v.P2VError):
+        p2v.parse_proof("{ not json", shape)
+    # field elements >= p and >= 2^64 are reduced like mkGoldilocks (Goldilocks.hs:132)
+    big = json.loads(json.dumps(proof)); big["proof"]["opening_proof"]["pow_witness"] = int(proof["proof"]["opening_proof"]["pow_witness"]) + 3 * P
+    assert np.array_equal(p2v.parse_proof(json.dumps(big), shape), blob)
+    common = json.loads(fixtures.read("small6", "common"))
+    c2 = json.loads(json.dumps(common)); c2["config"]["fri_config"]["reduction_strategy"] = {"MinSize": None}
+    with pytest.raises(p2v.P2VError) as e:
+        p2v.parse_common(json.dumps(c2))
+    assert e.value.code == -6  # "reduction strategy not implemented" (Plonk/FRI.hs:342)
+    c2 = json.loads(json.dumps(common)); c2["num_constants"] += 1
+    with pytest.raises(p2v.P2VError) as e:
+        p2v.parse_common(json.dumps(c2))
+    assert e.value.code == -5  # getSelectorConfig tally (Selector.hs:33-36)
