@@ -20,8 +20,11 @@
  *    ptr[j*n + i];
  *  - return value: 0 on success, a negative P2V_E_* code otherwise;
  *    p2v_last_error() gives the message.  No exception crosses the boundary;
- *  - one CUDA stream per context; calls on one context are serialised, different
- *    contexts may be used from different threads;
+ *  - one CUDA stream per context (non-blocking: it does NOT synchronise with the legacy
+ *    default stream); calls on one context are serialised, different contexts may be used
+ *    from different threads.  Device buffers handed to the library must be complete with
+ *    respect to that stream: a caller that filled them on another stream synchronises
+ *    first (or records an event and makes p2v_ctx_stream wait on it);
  *  - there is NO CPU fallback: without a usable sm_100 GPU p2v_ctx_create fails.
  */
 #ifndef P2V_H

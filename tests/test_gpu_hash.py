@@ -87,6 +87,7 @@ def test_merkle_device_pointers(ctx, orc):
     s = rand_felts(rng, (12, 4096))
     d_in = torch.from_numpy(s.view(np.int64)).cuda()
     d_out = torch.empty_like(d_in)
+    torch.cuda.synchronize()  # the H2D copy ran on torch's stream, the context has its own
     ctx.permutation(d_in, out=d_out)
     ctx.sync()
     got = d_out.cpu().numpy().view(np.uint64)

@@ -87,12 +87,13 @@ def test_chunked_and_device_resident(p2v, ctx, orc):
     ctx.set_chunk(64)
     acc1, st1 = cir.verifyProof(blobs)
     d_blobs = torch.from_numpy(blobs.view(np.int64)).cuda()
+    d_out = torch.empty((n, lay.blob_words), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()  # torch's stream -> the context's own stream
     acc2, st2 = cir.verifyProof(d_blobs, n=n)
     ctx.set_chunk(0)
     assert np.array_equal(st0, st1) and np.array_equal(st0, st2)
     assert np.array_equal(acc0, acc1) and np.array_equal(acc0, acc2)
     # device-side synthesis gives the same batch
-    d_out = torch.empty((n, lay.blob_words), dtype=torch.int64, device="cuda")
     cir.synth_batch(blob, n, words, deltas, d_out)
     ctx.sync()
     assert np.array_equal(d_out.cpu().numpy().view(np.uint64), blobs)
