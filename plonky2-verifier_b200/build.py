@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
 ]
+NVCC_FLAGS += os.environ.get("P2V_EXTRA_NVCC", "").split()  # tuning experiments only (e.g. -DPOSEIDON_SBOX_GROUP=12)
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-I", os.path.join(ROOT, "include")]
 
 

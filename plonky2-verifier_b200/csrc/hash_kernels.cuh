@@ -154,6 +154,7 @@ __global__ void k_cap_transpose(const u64 *__restrict__ level, u32 ncap, u64 *__
 //   mode 2: LOP3 + IMAD (32-bit mul.lo)
 //   mode 3: LOP3 + IADD3           (ALU pipe only)
 //   mode 4: IMAD.WIDE.U32 + IMAD.WIDE.U32 + LOP3
+//   mode 5: 2 x IMAD (32-bit)   6: 2 x LOP3   7: 1 x IMAD.WIDE.U32   8: 2 x SHF   9: IADD3 + IADD3.X (carry chain)
 // p2v_int_pipe_peak reports GROUPS per second (x32 threads).  If IMAD.WIDE issues every 2 cycles per
 // SM sub-partition, modes 0, 2 and 3 give the same rate (64 groups/clk/SM); mode 4 then runs at half
 // that rate, and if IMAD.WIDE were half rate mode 0 would already be at half.
@@ -177,8 +178,18 @@ __global__ void __launch_bounds__(256) k_int_pipe(u64 *out, u32 iters, u32 seed)
           asm volatile("{.reg .u32 lo,hi,t; mov.b64 {lo,hi},%0; xor.b32 t,lo,%1; mul.lo.u32 lo,t,%1; mov.b64 %0,{lo,hi};}" : "+l"(a[i]) : "r"(x));
         } else if (MODE == 3) {
           asm volatile("{.reg .u32 lo,hi,t; mov.b64 {lo,hi},%0; xor.b32 t,lo,%1; add.u32 lo,lo,t; mov.b64 %0,{lo,hi};}" : "+l"(a[i]) : "r"(x));
-        } else {
+        } else if (MODE == 4) {
           asm volatile("{.reg .u32 lo,hi,t; .reg .u64 w; mov.b64 {lo,hi},%0; xor.b32 t,lo,hi; mul.wide.u32 w,t,%1; mov.b64 {lo,hi},w; mul.wide.u32 %0,lo,hi;}" : "+l"(a[i]) : "r"(x));
+        } else if (MODE == 5) {  // 32-bit IMAD only (both halves are independent chains)
+          asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi},%0; mad.lo.u32 lo,lo,lo,%1; mad.lo.u32 hi,hi,hi,%1; mov.b64 %0,{lo,hi};}" : "+l"(a[i]) : "r"(x));
+        } else if (MODE == 6) {  // LOP3 only
+          asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi},%0; lop3.b32 lo,lo,hi,%1,0x96; lop3.b32 hi,hi,lo,%1,0xe8; mov.b64 %0,{lo,hi};}" : "+l"(a[i]) : "r"(x));
+        } else if (MODE == 7) {  // IMAD.WIDE only
+          asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi},%0; mul.wide.u32 %0,lo,hi;}" : "+l"(a[i]) : "r"(x));
+        } else if (MODE == 8) {  // funnel shifts only
+          asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi},%0; shf.l.wrap.b32 lo,lo,hi,%1; shf.r.wrap.b32 hi,hi,lo,%1; mov.b64 %0,{lo,hi};}" : "+l"(a[i]) : "r"(x));
+        } else {                 // 64-bit add with carry (IADD3 + IADD3.X)
+          asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi},%0; add.cc.u32 lo,lo,hi; addc.u32 hi,hi,%1; mov.b64 %0,{lo,hi};}" : "+l"(a[i]) : "r"(x));
         }
       }
     }

@@ -300,7 +300,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     P2V_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     // K6
     if (what & RUN_FRI) {
-      P2V_LAUNCH(ctx, k_fri_merkle, p2v_grid_for(ctx, m * d.Q * (4 + d.nsteps), 256, 3), 256, 0, d, ws, m);
+      P2V_LAUNCH(ctx, k_fri_merkle, p2v_grid_for(ctx, m * d.Q * (4 + d.nsteps), 256, P2V_MERKLE_MINBLOCKS), 256, 0, d, ws, m);
       P2V_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
       P2V_LAUNCH(ctx, k_fri_query, p2v_grid_for(ctx, m * d.Q, 256, 4), 256, 0, d, ws, m);
     }

@@ -246,7 +246,10 @@ __global__ void __launch_bounds__(128) k_challenges(const __grid_constant__ DevC
 // initial oracles (leaf = row of the oracle, path to the cap), trees 4.. are the commit-phase
 // trees (leaf = flattened coset evals).  ~97% of all permutations of a verification run here,
 // through a single permutation call site.
-__global__ void __launch_bounds__(256, 3) k_fri_merkle(const __grid_constant__ DevCircuit c, Workspace ws, size_t n) {
+#ifndef P2V_MERKLE_MINBLOCKS
+#define P2V_MERKLE_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, P2V_MERKLE_MINBLOCKS) k_fri_merkle(const __grid_constant__ DevCircuit c, Workspace ws, size_t n) {
   const int Q = c.Q;
   const size_t per_tree = n * (size_t)Q;
   const size_t total = per_tree * (size_t)(4 + c.nsteps);
