@@ -137,6 +137,7 @@ def lib():
         "p2v_fri": (C.c_int, [vp, vp, u64p, sz, u32p, u32p, u64p]),
         "p2v_verify_batch": (C.c_int, [vp, vp, u64p, sz, u32p, u32p]),
         "p2v_ctx_set_chunk": (C.c_int, [vp, sz]),
+        "p2v_ctx_set_pipeline": (C.c_int, [vp, C.c_int]),
         "p2v_synth_batch": (C.c_int, [vp, vp, u64p, sz, C.c_void_p, u64p, u64p]),
         "p2v_int_pipe_peak": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double)]),
         "p2v_ctx_last_ms": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_float)]),
@@ -155,7 +156,7 @@ EXPORTED_SYMBOLS = [
     "p2v_compress", "p2v_merkle_verify", "p2v_merkle_build", "p2v_merkle_open", "p2v_parse_common",
     "p2v_shape_free", "p2v_parse_gate", "p2v_shape_layout", "p2v_challenges_words", "p2v_parse_vkey",
     "p2v_parse_proof", "p2v_circuit_create", "p2v_circuit_destroy", "p2v_challenges", "p2v_constraints",
-    "p2v_fri", "p2v_verify_batch", "p2v_ctx_set_chunk", "p2v_synth_batch", "p2v_int_pipe_peak", "p2v_ctx_last_ms",
+    "p2v_fri", "p2v_verify_batch", "p2v_ctx_set_chunk", "p2v_ctx_set_pipeline", "p2v_synth_batch", "p2v_int_pipe_peak", "p2v_ctx_last_ms",
 ]
 
 
@@ -279,6 +280,9 @@ class Context:
 
     def set_chunk(self, n):
         self._check(lib().p2v_ctx_set_chunk(self._h, int(n)))
+
+    def set_pipeline(self, depth):
+        self._check(lib().p2v_ctx_set_pipeline(self._h, int(depth)))
 
     def last_ms(self, section):
         v = C.c_float()

@@ -13,6 +13,11 @@ struct p2v_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // second compute stream: chunk k+1's K0/K4/K5 overlap chunk k's K6
+  int pipeline = 2;                // 1 = strictly serial chunks (per-section timings valid), 2 = overlapped
+  void *ws2 = nullptr;
+  size_t ws2_bytes = 0;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
   std::string err;
   uint64_t launches = 0;
   size_t chunk = 0;  // proofs per pass; 0 = default
@@ -41,12 +46,13 @@ static inline int p2v_fail(p2v_ctx *ctx, int code, const std::string &msg) {
       return p2v_fail((ctx), P2V_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
   } while (0)
 
-#define P2V_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+#define P2V_LAUNCH_ON(ctx, strm, kernel, grid, block, smem, ...)                \
   do {                                                                          \
-    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);            \
+    kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                   \
     (ctx)->launches++;                                                          \
     P2V_CUDA((ctx), cudaGetLastError());                                        \
   } while (0)
+#define P2V_LAUNCH(ctx, kernel, grid, block, smem, ...) P2V_LAUNCH_ON(ctx, (ctx)->stream, kernel, grid, block, smem, __VA_ARGS__)
 
 static inline bool p2v_is_device_ptr(const void *p) {
   cudaPointerAttributes a;

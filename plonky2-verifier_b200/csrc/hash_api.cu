@@ -30,6 +30,9 @@ int p2v_ctx_create(int device, p2v_ctx **out) {
   ctx->sm_count = prop.multiProcessorCount;
   P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+  P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
   for (auto &ev : ctx->ev) P2V_CUDA(nullptr, cudaEventCreate(&ev));
   for (int i = 0; i < 2; i++) {
     P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming));
@@ -44,7 +47,12 @@ void p2v_ctx_destroy(p2v_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
+  cudaStreamSynchronize(ctx->stream2);
   if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->ws2) cudaFree(ctx->ws2);
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+  if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
+  cudaStreamDestroy(ctx->stream2);
   for (auto &b : ctx->stage_buf)
     if (b) cudaFree(b);
   for (auto &ev : ctx->ev)
@@ -67,6 +75,12 @@ int p2v_ctx_sync(p2v_ctx *ctx) {
 }
 
 uint64_t p2v_ctx_launch_count(const p2v_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int p2v_ctx_set_pipeline(p2v_ctx *ctx, int depth) {
+  if (!ctx || depth < 1 || depth > 2) return p2v_fail(ctx, P2V_E_INVALID, "p2v_ctx_set_pipeline: depth must be 1 or 2");
+  ctx->pipeline = depth;
+  return P2V_OK;
+}
 
 int p2v_ctx_set_chunk(p2v_ctx *ctx, size_t proofs_per_chunk) {
   if (!ctx) return P2V_E_INVALID;

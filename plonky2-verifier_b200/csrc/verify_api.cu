@@ -144,21 +144,24 @@ size_t carve(const DevCircuit &d, size_t m, char *base, Workspace *ws, bool want
   return off;
 }
 
-int ensureWorkspace(p2v_ctx *ctx, size_t bytes) {
-  if (ctx->ws_bytes >= bytes) return P2V_OK;
-  if (ctx->ws) {
+int ensureWorkspace(p2v_ctx *ctx, int which, size_t bytes) {
+  void *&ws = which ? ctx->ws2 : ctx->ws;
+  size_t &have = which ? ctx->ws2_bytes : ctx->ws_bytes;
+  if (have >= bytes) return P2V_OK;
+  if (ws) {
     P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->ws);
-    ctx->ws = nullptr;
-    ctx->ws_bytes = 0;
+    P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
+    cudaFree(ws);
+    ws = nullptr;
+    have = 0;
   }
-  cudaError_t e = cudaMalloc(&ctx->ws, bytes);
+  cudaError_t e = cudaMalloc(&ws, bytes);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return p2v_fail(ctx, P2V_E_NOMEM, "workspace allocation of " + std::to_string(bytes >> 20) + " MiB failed: " + cudaGetErrorString(e) +
                                           " (lower it with p2v_ctx_set_chunk)");
   }
-  ctx->ws_bytes = bytes;
+  have = bytes;
   return P2V_OK;
 }
 
@@ -244,23 +247,29 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   const DevCircuit &d = cir->dev;
   const size_t blob_words = (size_t)d.L.blob_words;
   bool src_dev = p2v_is_device_ptr(blobs);
+  // Chunking.  Serial mode: as few chunks as memory allows.  Pipelined mode (default): ~2 GiB chunks on two
+  // streams / two workspaces, so K0+K4+K5 of chunk k+1 (latency-bound, one thread per proof) fill the GPU
+  // next to the Merkle kernel of chunk k, and (host input) the H2D copy of chunk k+1 runs under chunk k.
   size_t chunk = ctx->chunk;
   if (chunk == 0) {
-    size_t budget = src_dev ? ((size_t)16 << 30) : ((size_t)1 << 30);
+    size_t budget = ctx->pipeline > 1 ? ((size_t)2 << 30) : (src_dev ? ((size_t)16 << 30) : ((size_t)2 << 30));
     chunk = budget / (blob_words * 8);
     if (chunk < 1024) chunk = 1024;
   }
   chunk = (chunk + 31) / 32 * 32;
   if (chunk > n) chunk = (n + 31) / 32 * 32;
+  const int depth = (ctx->pipeline > 1 && n > chunk) ? 2 : 1;
   bool want_folded = out.folded != nullptr;
   size_t ws_bytes = carve(d, chunk, nullptr, nullptr, want_folded);
   int rc;
-  if ((rc = ensureWorkspace(ctx, ws_bytes))) return rc;
-  Workspace ws;
-  carve(d, chunk, (char *)ctx->ws, &ws, want_folded);
+  Workspace wsp[2];
+  for (int k = 0; k < depth; k++) {
+    if ((rc = ensureWorkspace(ctx, k, ws_bytes))) return rc;
+    carve(d, chunk, (char *)(k ? ctx->ws2 : ctx->ws), &wsp[k], want_folded);
+  }
   if (!src_dev && (rc = ensureStage(ctx, chunk * blob_words * 8))) return rc;
 
-  // outputs that may live on the host
+  // outputs that may live on the host (temporaries are allocated in stream order on the primary stream)
   DevOut o_ch, o_comb, o_eq, o_status, o_bits, o_qs, o_folded;
   if ((rc = o_ch.init(ctx, out.challenges, (size_t)d.ch_words * n * 8))) return rc;
   if ((rc = o_comb.init(ctx, out.combined, (size_t)2 * d.r * n * 8))) return rc;
@@ -269,55 +278,73 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   if ((rc = o_bits.init(ctx, out.accept_bits, (n + 31) / 32 * 4))) return rc;
   if ((rc = o_qs.init(ctx, out.qstatus, n * d.Q * 4))) return rc;
   if ((rc = o_folded.init(ctx, out.folded, (size_t)2 * n * d.Q * 8))) return rc;
-
+  cudaStream_t streams[2] = {ctx->stream, ctx->stream2};
+  if (depth == 2) {
+    // fork: the second stream starts after everything already queued on the primary one
+    P2V_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+    P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->fork_ev, 0));
+  }
+  const bool timed = depth == 1;
   int k = 0;
   for (size_t c0 = 0; c0 < n; c0 += chunk, k++) {
     size_t m = std::min(chunk, n - c0);
     const u64 *src = blobs + c0 * blob_words;
     int b = k & 1;
+    cudaStream_t st = streams[depth == 2 ? b : 0];
+    Workspace &ws = wsp[depth == 2 ? b : 0];
     if (!src_dev) {
-      // double-buffered staging: the H2D copy of chunk k+1 overlaps the kernels of chunk k
+      // double-buffered staging: the H2D copy of chunk k+1 overlaps the kernels of chunk k; buffer b is free
+      // again once the K0 that read it (chunk k-2) has finished
       P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done[b], 0));
       P2V_CUDA(ctx, cudaMemcpyAsync(ctx->stage_buf[b], src, m * blob_words * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
       P2V_CUDA(ctx, cudaEventRecord(ctx->copy_done[b], ctx->copy_stream));
-      P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done[b], 0));
+      P2V_CUDA(ctx, cudaStreamWaitEvent(st, ctx->copy_done[b], 0));
       src = (const u64 *)ctx->stage_buf[b];
     }
     // K0
-    P2V_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     {
       dim3 grid((unsigned)((blob_words + 31) / 32), (unsigned)((m + 31) / 32));
-      P2V_LAUNCH(ctx, k_stage_transpose, grid, 256, 0, src, m, (int)blob_words, d.L.proof_words, d.L.query_words, d.Q, ws.pp, ws.qp);
+      P2V_LAUNCH_ON(ctx, st, k_stage_transpose, grid, 256, 0, src, m, (int)blob_words, d.L.proof_words, d.L.query_words, d.Q, ws.pp, ws.qp);
     }
-    if (!src_dev) P2V_CUDA(ctx, cudaEventRecord(ctx->compute_done[b], ctx->stream));
-    P2V_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (!src_dev) P2V_CUDA(ctx, cudaEventRecord(ctx->compute_done[b], st));
+    if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     // K4
-    P2V_LAUNCH(ctx, k_challenges, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
-    if (d.num_lookup_polys > 0) P2V_LAUNCH(ctx, k_lookup_delta_copies, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m);
-    P2V_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    P2V_LAUNCH_ON(ctx, st, k_challenges, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
+    if (d.num_lookup_polys > 0) P2V_LAUNCH_ON(ctx, st, k_lookup_delta_copies, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m);
+    if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     // K5
-    if (what & RUN_CONSTRAINTS) P2V_LAUNCH(ctx, k_constraints, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
-    P2V_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (what & RUN_CONSTRAINTS) P2V_LAUNCH_ON(ctx, st, k_constraints, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
+    if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     // K6
     if (what & RUN_FRI) {
-      P2V_LAUNCH(ctx, k_fri_merkle, p2v_grid_for(ctx, m * d.Q * (4 + d.nsteps), 256, P2V_MERKLE_MINBLOCKS), 256, 0, d, ws, m);
-      P2V_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
-      P2V_LAUNCH(ctx, k_fri_query, p2v_grid_for(ctx, m * d.Q, 256, 4), 256, 0, d, ws, m);
+      size_t items = m * (size_t)d.Q * (4 + d.nsteps);
+      // serial mode: persistent grid; pipelined mode: one block per 256 openings, so that blocks of the two
+      // streams' kernels interleave on the SMs as resources free up
+      unsigned grid = depth == 2 ? (unsigned)((items + 255) / 256) : (unsigned)p2v_grid_for(ctx, items, 256, P2V_MERKLE_MINBLOCKS);
+      P2V_LAUNCH_ON(ctx, st, k_fri_merkle, grid, 256, 0, d, ws, m);
+      if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
+      P2V_LAUNCH_ON(ctx, st, k_fri_query, p2v_grid_for(ctx, m * d.Q, 256, 4), 256, 0, d, ws, m);
     }
-    P2V_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
     // K7
     if (out.verdict_mode) {
-      u32 *st = o_status.as<u32>() ? o_status.as<u32>() + c0 : nullptr;
+      u32 *stp = o_status.as<u32>() ? o_status.as<u32>() + c0 : nullptr;
       u32 *bits = o_bits.as<u32>() ? o_bits.as<u32>() + c0 / 32 : nullptr;
-      P2V_LAUNCH(ctx, k_verdict, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m, out.verdict_mode, st, bits);
+      P2V_LAUNCH_ON(ctx, st, k_verdict, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m, out.verdict_mode, stp, bits);
     }
-    P2V_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+    if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
     // optional intermediate outputs
-    if (o_ch.dev) P2V_LAUNCH(ctx, k_copy_planes, p2v_grid_for(ctx, m * d.ch_words, 256, 8), 256, 0, ws.ch, m, d.ch_words, o_ch.as<u64>(), n, c0);
-    if (o_comb.dev) P2V_LAUNCH(ctx, k_copy_planes, p2v_grid_for(ctx, m * 2 * d.r, 256, 8), 256, 0, ws.comb, m, 2 * d.r, o_comb.as<u64>(), n, c0);
-    if (o_eq.dev) P2V_LAUNCH(ctx, k_copy_bytes, p2v_grid_for(ctx, m, 256, 8), 256, 0, ws.eqmask, m, o_eq.as<uint8_t>() + c0);
-    if (o_qs.dev) P2V_LAUNCH(ctx, k_copy_qstat, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.qstat, m, d.Q, o_qs.as<u32>(), c0);
-    if (o_folded.dev) P2V_LAUNCH(ctx, k_copy_folded, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.folded, m, d.Q, o_folded.as<u64>(), n, c0);
+    if (o_ch.dev) P2V_LAUNCH_ON(ctx, st, k_copy_planes, p2v_grid_for(ctx, m * d.ch_words, 256, 8), 256, 0, ws.ch, m, d.ch_words, o_ch.as<u64>(), n, c0);
+    if (o_comb.dev) P2V_LAUNCH_ON(ctx, st, k_copy_planes, p2v_grid_for(ctx, m * 2 * d.r, 256, 8), 256, 0, ws.comb, m, 2 * d.r, o_comb.as<u64>(), n, c0);
+    if (o_eq.dev) P2V_LAUNCH_ON(ctx, st, k_copy_bytes, p2v_grid_for(ctx, m, 256, 8), 256, 0, ws.eqmask, m, o_eq.as<uint8_t>() + c0);
+    if (o_qs.dev) P2V_LAUNCH_ON(ctx, st, k_copy_qstat, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.qstat, m, d.Q, o_qs.as<u32>(), c0);
+    if (o_folded.dev) P2V_LAUNCH_ON(ctx, st, k_copy_folded, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.folded, m, d.Q, o_folded.as<u64>(), n, c0);
+  }
+  if (depth == 2) {
+    // join: whoever orders work after us on the primary stream (D2H below, the caller's events, NCCL) sees both
+    P2V_CUDA(ctx, cudaEventRecord(ctx->join_ev, ctx->stream2));
+    P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
   }
   bool any_host = false;
   for (DevOut *o : {&o_ch, &o_comb, &o_eq, &o_status, &o_bits, &o_qs, &o_folded}) {
@@ -328,7 +355,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   ctx->last_ms.clear();
-  ctx->last_ms["_pending"] = 1.0f;
+  if (timed) ctx->last_ms["_pending"] = 1.0f;
   return P2V_OK;
 }
 

@@ -85,12 +85,21 @@ def test_chunked_and_device_resident(p2v, ctx, orc):
     blobs, words, deltas = fixtures.tampered_batch(blob, lay, shape, n, seed=3)
     acc0, st0 = cir.verifyProof(blobs)
     ctx.set_chunk(64)
-    acc1, st1 = cir.verifyProof(blobs)
+    acc1, st1 = cir.verifyProof(blobs)       # 4 chunks on the two-stream pipeline (default depth 2)
+    ctx.set_pipeline(1)
+    acc3, st3 = cir.verifyProof(blobs)       # same chunks, strictly serial
+    ctx.set_pipeline(2)
+    assert np.array_equal(st1, st3) and np.array_equal(acc1, acc3)
+    ch_p = cir.proofChallenges(blobs)        # debug outputs gathered across pipelined chunks
+    st_p, qs_p, fold_p = cir.checkFRIProof(blobs, want_debug=True)
     d_blobs = torch.from_numpy(blobs.view(np.int64)).cuda()
     d_out = torch.empty((n, lay.blob_words), dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()  # torch's stream -> the context's own stream
     acc2, st2 = cir.verifyProof(d_blobs, n=n)
     ctx.set_chunk(0)
+    st_1, qs_1, fold_1 = cir.checkFRIProof(blobs, want_debug=True)
+    assert np.array_equal(ch_p, cir.proofChallenges(blobs))
+    assert np.array_equal(st_p, st_1) and np.array_equal(qs_p, qs_1) and np.array_equal(fold_p, fold_1)
     assert np.array_equal(st0, st1) and np.array_equal(st0, st2)
     assert np.array_equal(acc0, acc1) and np.array_equal(acc0, acc2)
     # device-side synthesis gives the same batch
