@@ -274,7 +274,8 @@ int p2v_synth_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *template
 /* ---- measurement helpers ------------------------------------------------------- */
 /* Integer-pipe peak microbenchmark: dependent chains whose every step is a GROUP of instructions:
  * mode 0: LOP3 + IMAD.WIDE.U32, 1: 2 LOP3 + IMAD.WIDE.U32, 2: LOP3 + IMAD (32-bit), 3: LOP3 + IADD3,
- * 4: 2 IMAD.WIDE.U32 + LOP3, 5: 2 IMAD (32-bit), 6: 2 LOP3, 7: IMAD.WIDE.U32 alone, 8: 2 SHF, 9: IADD3 + IADD3.X.
+ * 4: 2 IMAD.WIDE.U32 + LOP3, 5: 2 IMAD (32-bit), 6: 2 LOP3, 7: IMAD.WIDE.U32 alone, 8: 2 SHF, 9: IADD3 + IADD3.X,
+ * 10: DFMA, 11: DFMA + LOP3 + IMAD, 12: DADD.
  * *ops_per_s = groups per second summed over all threads. */
 int p2v_int_pipe_peak(p2v_ctx *ctx, int mode, double *ops_per_s);
 /* Device time (ms) of a section of the most recent batch call (last chunk): "stage" (K0), "challenges" (K4),

@@ -238,7 +238,7 @@ int p2v_merkle_open(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, uint32_t l
 
 // ---- measurement helper -------------------------------------------------------------------
 int p2v_int_pipe_peak(p2v_ctx *ctx, int mode, double *ops_per_s) {
-  if (!ctx || !ops_per_s || mode < 0 || mode > 9) return p2v_fail(ctx, P2V_E_INVALID, "p2v_int_pipe_peak: bad argument");
+  if (!ctx || !ops_per_s || mode < 0 || mode > 12) return p2v_fail(ctx, P2V_E_INVALID, "p2v_int_pipe_peak: bad argument");
   P2V_CUDA(ctx, cudaSetDevice(ctx->device));
   u64 *d = nullptr;
   P2V_CUDA(ctx, cudaMalloc(&d, 8));
@@ -257,7 +257,10 @@ int p2v_int_pipe_peak(p2v_ctx *ctx, int mode, double *ops_per_s) {
       case 6: P2V_LAUNCH(ctx, k_int_pipe<6>, grid, block, 0, d, iters, 12345u); break;
       case 7: P2V_LAUNCH(ctx, k_int_pipe<7>, grid, block, 0, d, iters, 12345u); break;
       case 8: P2V_LAUNCH(ctx, k_int_pipe<8>, grid, block, 0, d, iters, 12345u); break;
-      default: P2V_LAUNCH(ctx, k_int_pipe<9>, grid, block, 0, d, iters, 12345u); break;
+      case 9: P2V_LAUNCH(ctx, k_int_pipe<9>, grid, block, 0, d, iters, 12345u); break;
+      case 10: P2V_LAUNCH(ctx, k_int_pipe<10>, grid, block, 0, d, iters, 12345u); break;
+      case 11: P2V_LAUNCH(ctx, k_int_pipe<11>, grid, block, 0, d, iters, 12345u); break;
+      default: P2V_LAUNCH(ctx, k_int_pipe<12>, grid, block, 0, d, iters, 12345u); break;
     }
     P2V_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     P2V_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));

@@ -155,6 +155,7 @@ __global__ void k_cap_transpose(const u64 *__restrict__ level, u32 ncap, u64 *__
 //   mode 3: LOP3 + IADD3           (ALU pipe only)
 //   mode 4: IMAD.WIDE.U32 + IMAD.WIDE.U32 + LOP3
 //   mode 5: 2 x IMAD (32-bit)   6: 2 x LOP3   7: 1 x IMAD.WIDE.U32   8: 2 x SHF   9: IADD3 + IADD3.X (carry chain)
+//   mode 10: DFMA   11: DFMA + LOP3 + IMAD (three pipes)   12: DADD
 // p2v_int_pipe_peak reports GROUPS per second (x32 threads).  If IMAD.WIDE issues every 2 cycles per
 // SM sub-partition, modes 0, 2 and 3 give the same rate (64 groups/clk/SM); mode 4 then runs at half
 // that rate, and if IMAD.WIDE were half rate mode 0 would already be at half.
@@ -162,8 +163,16 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_int_pipe(u64 *out, u32 iters, u32 seed) {
   u32 x = threadIdx.x * 2654435761u + seed;
   u64 a[8];
+  u32 b[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) a[i] = (u64)x * (i + 3) + i;
+  for (int i = 0; i < 8; i++) {
+    a[i] = (u64)x * (i + 3) + i;
+    b[i] = x * (i + 7);
+  }
+  if (MODE >= 10) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = 0x3FF0000000000000ULL | (a[i] & 0xFFFFFFFFFULL);  // doubles in [1,2)
+  }
 #pragma unroll 1
   for (u32 it = 0; it < iters; it++) {
 #pragma unroll
@@ -188,14 +197,21 @@ __global__ void __launch_bounds__(256) k_int_pipe(u64 *out, u32 iters, u32 seed)
           asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi},%0; mul.wide.u32 %0,lo,hi;}" : "+l"(a[i]) : "r"(x));
         } else if (MODE == 8) {  // funnel shifts only
           asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi},%0; shf.l.wrap.b32 lo,lo,hi,%1; shf.r.wrap.b32 hi,hi,lo,%1; mov.b64 %0,{lo,hi};}" : "+l"(a[i]) : "r"(x));
-        } else {                 // 64-bit add with carry (IADD3 + IADD3.X)
+        } else if (MODE == 9) {  // 64-bit add with carry (IADD3 + IADD3.X)
           asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi},%0; add.cc.u32 lo,lo,hi; addc.u32 hi,hi,%1; mov.b64 %0,{lo,hi};}" : "+l"(a[i]) : "r"(x));
+        } else if (MODE == 10) {  // DFMA only (FP64 pipe)
+          asm volatile("{.reg .f64 d; mov.b64 d,%0; fma.rn.f64 d,d,0d3FF0000000000001,0d3FF8000000000000; mov.b64 %0,d;}" : "+l"(a[i]));
+        } else if (MODE == 11) {  // DFMA + IMAD32 + LOP3: three pipes
+          asm volatile("{.reg .f64 d; mov.b64 d,%0; fma.rn.f64 d,d,0d3FF0000000000001,0d3FF8000000000000; mov.b64 %0,d;}" : "+l"(a[i]));
+          asm volatile("{.reg .u32 t; xor.b32 t,%0,%1; mul.lo.u32 %0,t,%1;}" : "+r"(b[i]) : "r"(x));
+        } else {                  // DADD only
+          asm volatile("{.reg .f64 d; mov.b64 d,%0; add.rn.f64 d,d,0d3FF8000000000000; mov.b64 %0,d;}" : "+l"(a[i]));
         }
       }
     }
   }
   u64 acc = 0;
 #pragma unroll
-  for (int i = 0; i < 8; i++) acc += a[i];
+  for (int i = 0; i < 8; i++) acc += a[i] + b[i];
   if (acc == 0x1234567812345678ULL) out[0] = acc;  // keep the chains alive
 }

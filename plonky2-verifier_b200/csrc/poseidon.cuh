@@ -134,6 +134,74 @@ __device__ __forceinline__ void poseidon_mds(u64 (&s)[12], int next_round) {
   poseidon_mds_row<0>(s, l0, l1, l2, next_round);
 }
 
+// ---- alternative linear layer on the FP64 pipe ---------------------------------------------------------------
+// B200 has a full-rate FP64 pipe (64 DFMA/clk/SM) that integer code leaves idle.  The MDS layer is a sum of
+// small-constant products, and a double holds integers < 2^53 exactly, so the layer can run there while the
+// FMA pipe (IMAD / IMAD.WIDE of the s-boxes) and the ALU pipe do the rest:
+//   lo_j, hi_j = the 32-bit halves of s_j as doubles (exact: u32 -> double by the 2^52 trick)
+//   L_i = rc_lo + sum_j M[i][j]*lo_j   (< 2^41),   H_i likewise          288 DFMAs per layer, all exact
+//   back to integers with the same trick (mantissa of x + 2^52), then value = L + 2^32*H reduced once:
+//   L = Ll + 2^32*Lh, H = Hl + 2^32*Hh (Lh,Hh < 2^10):  w0 = Ll, w1 = Lh + Hl, w2 = Hh + carry,
+//   (w1:w0) + w2*2^64 == (w1 + w2 : w0) - w2  (mod p), a wrap of w1 + w2 adds another 2^32 - 1.
+struct PoseidonRcF64 {
+  double v[31][12][2];
+};
+constexpr PoseidonRcF64 poseidon_make_rc_f64() {
+  constexpr u64 rc[360] = P2V_ALL_ROUND_CONSTANTS;
+  PoseidonRcF64 t{};
+  for (int r = 0; r < 30; r++)
+    for (int i = 0; i < 12; i++) {
+      t.v[r][i][0] = (double)(rc[r * 12 + i] & 0xFFFFFFFFULL);
+      t.v[r][i][1] = (double)(rc[r * 12 + i] >> 32);
+    }
+  return t;
+}
+static __constant__ PoseidonRcF64 c_rcd = poseidon_make_rc_f64();
+
+#define P2V_TWO52 4503599627370496.0
+__device__ __forceinline__ double poseidon_u32_to_f64(u32 x) { return __hiloint2double(0x43300000, (int)x) - P2V_TWO52; }
+
+template <int I, int J>
+__device__ __forceinline__ void poseidon_mds_acc_f64(double &L, double &H, const double (&lo)[12], const double (&hi)[12]) {
+  constexpr u32 C[12] = POSEIDON_MDS_ROW;
+  constexpr double c = (double)(C[(J - I + 12) % 12] + ((I == 0 && J == 0) ? 8u : 0u));
+  L = fma(lo[J], c, L);
+  H = fma(hi[J], c, H);
+  if constexpr (J + 1 < 12) poseidon_mds_acc_f64<I, J + 1>(L, H, lo, hi);
+}
+template <int I>
+__device__ __forceinline__ void poseidon_mds_row_f64(u64 (&s)[12], const double (&lo)[12], const double (&hi)[12], int next_round) {
+  double L = c_rcd.v[next_round][I][0], H = c_rcd.v[next_round][I][1];
+  poseidon_mds_acc_f64<I, 0>(L, H, lo, hi);
+  L += P2V_TWO52;
+  H += P2V_TWO52;
+  u32 Ll = (u32)__double2loint(L), Lh = (u32)__double2hiint(L) & 0xFFFFFu;
+  u32 Hl = (u32)__double2loint(H), Hh = (u32)__double2hiint(H) & 0xFFFFFu;
+  u32 r0, r1;
+  asm("{\n\t.reg .u32 w2,c;\n\t"
+      "add.cc.u32 %1,%3,%4;\n\taddc.u32 w2,%5,0;\n\t"       // w1 = Lh + Hl, w2 = Hh + carry
+      "add.cc.u32 %1,%1,w2;\n\taddc.u32 c,0,0;\n\t"         // w1 += w2, c = wrap
+      "add.u32 w2,w2,c;\n\tadd.u32 %1,%1,c;\n\t"
+      "sub.cc.u32 %0,%2,w2;\n\tsubc.u32 %1,%1,0;\n\t}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"(Ll), "r"(Lh), "r"(Hl), "r"(Hh));
+  s[I] = ((u64)r1 << 32) | r0;
+  if constexpr (I + 1 < 12) poseidon_mds_row_f64<I + 1>(s, lo, hi, next_round);
+}
+__device__ __forceinline__ void poseidon_mds_f64(u64 (&s)[12], int next_round) {
+  double lo[12], hi[12];
+#pragma unroll
+  for (int j = 0; j < 12; j++) {
+    lo[j] = poseidon_u32_to_f64((u32)s[j]);
+    hi[j] = poseidon_u32_to_f64((u32)(s[j] >> 32));
+  }
+  poseidon_mds_row_f64<0>(s, lo, hi, next_round);
+}
+
+#ifndef POSEIDON_MDS_F64
+#define POSEIDON_MDS_F64 1
+#endif
+
 // The permutation.  Input: lazy u64 (any values); output: lazy u64 (apply gl_canon before use as data).
 __device__ __forceinline__ void poseidon_permute(u64 (&s)[12]) {
 #pragma unroll
@@ -156,6 +224,10 @@ __device__ __forceinline__ void poseidon_permute(u64 (&s)[12]) {
     } else {
       s[0] = poseidon_sbox(s[0]);
     }
+#if POSEIDON_MDS_F64
+    poseidon_mds_f64(s, r + 1);
+#else
     poseidon_mds(s, r + 1);
+#endif
   }
 }
