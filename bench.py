@@ -175,6 +175,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: libp2v has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    from plonky2_verifier_b200 import sharding
+    prev_affinity = sharding.bind_to_gpu_numa_node(local_rank)  # pinned staging buffers on the GPU's NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -295,6 +297,16 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = n_e2e * world * e2e_steps / float(te.item())
     assert np.array_equal(h_status, status_host[:n_e2e]), "host-buffer path and device-resident path disagree"
+    # raw pinned-host -> device copy bandwidth of this box (what bounds the end-to-end path)
+    probe_n = min(n_e2e, 16384)
+    d_probe = torch.empty((probe_n, W), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        d_probe.copy_(h_blobs_t[:probe_n], non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * probe_n * W * 8 / (time.perf_counter() - t0) / 1e9
+    del d_probe
 
     if rank != 0:
         if dist is not None:
@@ -317,6 +329,7 @@ def main():
     hbm_achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
 
     cpu = None
+    os.sched_setaffinity(0, prev_affinity)  # the CPU baseline gets every host core again
     if not args.no_cpu_baseline:
         cpu, cpu_res, sample = cpu_baseline(shape, lay, vkey, sched_blobs)
         # the sample is also a parity check of the timed batch (same schedule => same verdicts)
@@ -333,9 +346,10 @@ def main():
                    "proofs_per_gpu": n, "blob_bytes": W * 8, "queries": shape.num_queries, "perms_per_proof": 114 + shape.num_queries * ppq,
                    "l2": "inputs (%.1f GB per step) are far larger than L2" % (n * W * 8 / 1e9),
                    "batch": "bundled S12 fixture x %d, 3 of 4 copies tampered in one word" % n,
-                   "verdict_histogram": hist, "pipeline": "2 streams x 2 GiB chunks (K0/K4/K5 of chunk k+1 overlap K6 of chunk k)", "multi_gpu": "contiguous slices + NCCL all_gather of the accept bitmap" if world > 1 else "single GPU"},
+                   "verdict_histogram": hist, "host_numa": "process bound to the GPU's NUMA node (%d cpus) for the pinned staging buffers" % len(os.sched_getaffinity(0)), "pipeline": "2 streams x 2 GiB chunks (K0/K4/K5 of chunk k+1 overlap K6 of chunk k)", "multi_gpu": "contiguous slices + NCCL all_gather of the accept bitmap" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * W * 8, "d2h_bytes_per_step": int(h_bits.nbytes + h_status.nbytes),
-                "proofs_per_gpu": n_e2e},
+                "proofs_per_gpu": n_e2e, "h2d_copy_gbs_measured": h2d_gbs,
+                "h2d_bound_proofs_per_s": h2d_gbs * 1e9 / (W * 8) * world},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "int_pipe", "kernel": "k_fri_merkle", "achieved": achieved / 1e9, "peak": imad_peak / 1e9, "unit": "GIMAD/s",

@@ -198,8 +198,69 @@ __device__ __forceinline__ void poseidon_mds_f64(u64 (&s)[12], int next_round) {
   poseidon_mds_row_f64<0>(s, lo, hi, next_round);
 }
 
+// ---- mixed linear layer: low 43 bits on the FP64 pipe, high 21 bits on 32-bit IMADs -----------------------
+// x = lo43 + 2^43*hi21.  L_i = rc_lo43 + sum_j M[i][j]*lo43_j < 264*2^43 + 2^43 < 2^52 is exact in a double and
+// still extractable with the 2^52 trick; H_i = rc_hi21 + sum_j M[i][j]*hi21_j < 2^30 fits a 32-bit IMAD chain.
+// Same 288 multiply-adds per layer as the pure FP64 form, but split across two pipes.
+//   value = L + 2^43*H:  w0 = L[31:0], w1 = L[51:32] + (H << 11)[31:0], w2 = (H >> 21) + carry  (< 2^10)
+struct PoseidonRcMixed {
+  double lo[31][12];
+  u32 hi[31][12];
+};
+constexpr PoseidonRcMixed poseidon_make_rc_mixed() {
+  constexpr u64 rc[360] = P2V_ALL_ROUND_CONSTANTS;
+  PoseidonRcMixed t{};
+  for (int r = 0; r < 30; r++)
+    for (int i = 0; i < 12; i++) {
+      t.lo[r][i] = (double)(rc[r * 12 + i] & ((1ULL << 43) - 1));
+      t.hi[r][i] = (u32)(rc[r * 12 + i] >> 43);
+    }
+  return t;
+}
+static __constant__ PoseidonRcMixed c_rcm = poseidon_make_rc_mixed();
+
+template <int I, int J>
+__device__ __forceinline__ void poseidon_mds_acc_mixed(double &L, u32 &H, const double (&lo)[12], const u32 (&hi)[12]) {
+  constexpr u32 C[12] = POSEIDON_MDS_ROW;
+  constexpr u32 ci = C[(J - I + 12) % 12] + ((I == 0 && J == 0) ? 8u : 0u);
+  constexpr double c = (double)ci;
+  L = fma(lo[J], c, L);
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(H) : "r"(hi[J]), "n"(ci));
+  if constexpr (J + 1 < 12) poseidon_mds_acc_mixed<I, J + 1>(L, H, lo, hi);
+}
+template <int I>
+__device__ __forceinline__ void poseidon_mds_row_mixed(u64 (&s)[12], const double (&lo)[12], const u32 (&hi)[12], int next_round) {
+  double L = c_rcm.lo[next_round][I];
+  u32 H = c_rcm.hi[next_round][I];
+  poseidon_mds_acc_mixed<I, 0>(L, H, lo, hi);
+  L += P2V_TWO52;
+  u32 Ll = (u32)__double2loint(L), Lh = (u32)__double2hiint(L) & 0xFFFFFu;
+  u32 r0, r1;
+  asm("{\n\t.reg .u32 t,w2,c;\n\t"
+      "shl.b32 t,%4,11;\n\tadd.cc.u32 %1,%3,t;\n\t"          // w1 = Lh + (H << 11)
+      "shr.u32 w2,%4,21;\n\taddc.u32 w2,w2,0;\n\t"           // w2 = (H >> 21) + carry
+      "add.cc.u32 %1,%1,w2;\n\taddc.u32 c,0,0;\n\t"
+      "add.u32 w2,w2,c;\n\tadd.u32 %1,%1,c;\n\t"
+      "sub.cc.u32 %0,%2,w2;\n\tsubc.u32 %1,%1,0;\n\t}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"(Ll), "r"(Lh), "r"(H));
+  s[I] = ((u64)r1 << 32) | r0;
+  if constexpr (I + 1 < 12) poseidon_mds_row_mixed<I + 1>(s, lo, hi, next_round);
+}
+__device__ __forceinline__ void poseidon_mds_mixed(u64 (&s)[12], int next_round) {
+  double lo[12];
+  u32 hi[12];
+#pragma unroll
+  for (int j = 0; j < 12; j++) {
+    u32 xl = (u32)s[j], xh = (u32)(s[j] >> 32);
+    lo[j] = __hiloint2double((int)(0x43300000u | (xh & 0x7FFu)), (int)xl) - P2V_TWO52;  // lo43 as a double, exact
+    hi[j] = xh >> 11;
+  }
+  poseidon_mds_row_mixed<0>(s, lo, hi, next_round);
+}
+
 #ifndef POSEIDON_MDS_F64
-#define POSEIDON_MDS_F64 1
+#define POSEIDON_MDS_F64 2
 #endif
 
 // The permutation.  Input: lazy u64 (any values); output: lazy u64 (apply gl_canon before use as data).
@@ -224,7 +285,9 @@ __device__ __forceinline__ void poseidon_permute(u64 (&s)[12]) {
     } else {
       s[0] = poseidon_sbox(s[0]);
     }
-#if POSEIDON_MDS_F64
+#if POSEIDON_MDS_F64 == 2
+    poseidon_mds_mixed(s, r + 1);
+#elif POSEIDON_MDS_F64
     poseidon_mds_f64(s, r + 1);
 #else
     poseidon_mds(s, r + 1);

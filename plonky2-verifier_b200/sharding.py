@@ -68,3 +68,35 @@ def verify_batch_sharded(circuit, blobs_local, n_total, rank, world, dist=None, 
     else:
         full = bits[: (n_total + 31) // 32]
     return full, status[:n_local]
+
+
+def gpu_numa_cpus(device):
+    """CPUs of the NUMA node the GPU hangs off (None if the topology cannot be read).  Pinned staging buffers
+    that are first-touched from these CPUs sit on the GPU's own node; on a two-socket host the other placement
+    halves the H2D bandwidth of the end-to-end path."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        return cpus or None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(device):
+    """Restrict this process to the CPUs next to `device`; returns the previous affinity (for os.sched_setaffinity)."""
+    import os
+
+    prev = os.sched_getaffinity(0)
+    cpus = gpu_numa_cpus(device)
+    if cpus and (cpus & prev):
+        os.sched_setaffinity(0, cpus & prev)
+    return prev
