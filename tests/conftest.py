@@ -11,13 +11,20 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    _ensure_built()  # fixtures.load() parses the bundled JSON with the product's host parser
+
+
+def _ensure_built():
+    """Build libp2v.so in-tree when it is missing or stale (nvcc cross-compiles without a GPU; ~1 min once)."""
+    import plonky2_verifier_b200 as m
+
+    m.build()
+    return m
 
 
 @pytest.fixture(scope="session")
 def p2v():
-    import plonky2_verifier_b200 as m
-
-    return m
+    return _ensure_built()
 
 
 @pytest.fixture(scope="session")
