@@ -219,6 +219,9 @@ constexpr PoseidonRcMixed poseidon_make_rc_mixed() {
 }
 static __constant__ PoseidonRcMixed c_rcm = poseidon_make_rc_mixed();
 
+// Accumulation order: inputs 1..11 first, input 0 LAST.  In a partial round only lane 0 comes out of an s-box
+// (a ~100-cycle dependent chain on the FMA pipe); with this order the 11/12 of the layer that do not depend on
+// it (DFMA + IMAD chains) are independent work the scheduler can interleave with that chain.
 template <int I, int J>
 __device__ __forceinline__ void poseidon_mds_acc_mixed(double &L, u32 &H, const double (&lo)[12], const u32 (&hi)[12]) {
   constexpr u32 C[12] = POSEIDON_MDS_ROW;
@@ -226,13 +229,15 @@ __device__ __forceinline__ void poseidon_mds_acc_mixed(double &L, u32 &H, const 
   constexpr double c = (double)ci;
   L = fma(lo[J], c, L);
   asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(H) : "r"(hi[J]), "n"(ci));
-  if constexpr (J + 1 < 12) poseidon_mds_acc_mixed<I, J + 1>(L, H, lo, hi);
+  if constexpr (J == 0) return;
+  else if constexpr (J + 1 < 12) poseidon_mds_acc_mixed<I, J + 1>(L, H, lo, hi);
+  else poseidon_mds_acc_mixed<I, 0>(L, H, lo, hi);
 }
 template <int I>
-__device__ __forceinline__ void poseidon_mds_row_mixed(u64 (&s)[12], const double (&lo)[12], const u32 (&hi)[12], int next_round) {
+__device__ __forceinline__ void poseidon_mds_row_mixed(u64 (&s)[12], const double (&lo)[12], const u32 (&hi)[12], int next_round) {  // s = output
   double L = c_rcm.lo[next_round][I];
   u32 H = c_rcm.hi[next_round][I];
-  poseidon_mds_acc_mixed<I, 0>(L, H, lo, hi);
+  poseidon_mds_acc_mixed<I, 1>(L, H, lo, hi);
   L += P2V_TWO52;
   u32 Ll = (u32)__double2loint(L), Lh = (u32)__double2hiint(L) & 0xFFFFFu;
   u32 r0, r1;
@@ -256,9 +261,19 @@ __device__ __forceinline__ void poseidon_mds_mixed(u64 (&s)[12], int next_round)
     lo[j] = __hiloint2double((int)(0x43300000u | (xh & 0x7FFu)), (int)xl) - P2V_TWO52;  // lo43 as a double, exact
     hi[j] = xh >> 11;
   }
+#if POSEIDON_MDS_SEPARATE_OUT
+  u64 o[12];
+  poseidon_mds_row_mixed<0>(o, lo, hi, next_round);
+#pragma unroll
+  for (int j = 0; j < 12; j++) s[j] = o[j];
+#else
   poseidon_mds_row_mixed<0>(s, lo, hi, next_round);
+#endif
 }
 
+#ifndef POSEIDON_MDS_SEPARATE_OUT
+#define POSEIDON_MDS_SEPARATE_OUT 0
+#endif
 #ifndef POSEIDON_MDS_F64
 #define POSEIDON_MDS_F64 2
 #endif
