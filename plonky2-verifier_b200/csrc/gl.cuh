@@ -45,17 +45,28 @@ __device__ __forceinline__ u64 gl_sub(u64 a, u64 b) {
 }
 __device__ __forceinline__ u64 gl_neg(u64 a) { return gl_sub(0, a); }
 
-// (hi:lo) mod p, 128-bit input, lazy 64-bit output.
+// (hi:lo) mod p, 128-bit input, lazy 64-bit output: carry-chain form (13 integer ops, no compares/selects)
+//   t = (w1:w0) - w3, minus EPS on borrow;  u = w2*(2^32-1) = (w2<<32) - w2;  r = t + u, plus EPS on carry.
+// Neither correction can wrap twice: after a borrow t >= 2^64 - 2^32 + 1, and a wrapped r is < u <= 2^64 - 2^33 + 1.
+// NOTE on flags: `subc m,0,0` right after a SUB chain yields the borrow mask, but after an ADD chain ptxas feeds the
+// raw hardware carry into it (inverted meaning), so carries are materialised with addc + neg instead.
 __device__ __forceinline__ u64 gl_reduce128(u64 lo, u64 hi) {
-  u32 hh = (u32)(hi >> 32), hl = (u32)hi;
-  u64 t = lo - hh;
-  if (lo < hh) t -= GL_EPS;  // cannot wrap twice: t >= 2^64 - 2^32 + 1 here
-  u64 u = (u64)hl * 0xFFFFFFFFu;  // < 2^64 - 2^33 + 2
-  u64 r = t + u;
-  if (r < u) r += GL_EPS;  // wrapped r < u <= 2^64 - 2^33 + 1, so no second wrap
-  return r;
+  u32 w0 = (u32)lo, w1 = (u32)(lo >> 32), w2 = (u32)hi, w3 = (u32)(hi >> 32), r0, r1;
+  asm("{\n\t.reg .u32 m,t0,t1,u0,u1;\n\t"
+      "sub.cc.u32 t0,%2,%5;\n\tsubc.cc.u32 t1,%3,0;\n\tsubc.u32 m,0,0;\n\t"
+      "sub.cc.u32 t0,t0,m;\n\tsubc.u32 t1,t1,0;\n\t"
+      "sub.cc.u32 u0,0,%4;\n\tsubc.u32 u1,%4,0;\n\t"
+      "add.cc.u32 t0,t0,u0;\n\taddc.cc.u32 t1,t1,u1;\n\taddc.u32 m,0,0;\n\tneg.s32 m,m;\n\t"
+      "add.cc.u32 %0,t0,m;\n\taddc.u32 %1,t1,0;\n\t}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(w0), "r"(w1), "r"(w2), "r"(w3));
+  return ((u64)r1 << 32) | r0;
 }
-__device__ __forceinline__ u64 gl_mul(u64 a, u64 b) { return gl_reduce128(a * b, __umul64hi(a, b)); }
+// one 128-bit product: ptxas shares the partial products between the low and the high half (4 IMAD.WIDE + 3)
+__device__ __forceinline__ u64 gl_mul(u64 a, u64 b) {
+  unsigned __int128 m = (unsigned __int128)a * b;
+  return gl_reduce128((u64)m, (u64)(m >> 64));
+}
 __device__ __forceinline__ u64 gl_sqr(u64 a) { return gl_mul(a, a); }
 // a * small constant c (c < 2^32)
 __device__ __forceinline__ u64 gl_mul_small(u64 a, u32 c) {

@@ -60,35 +60,12 @@ static __constant__ PoseidonRcLimbs c_rc3 = poseidon_make_rc_limbs();
 #define POSEIDON_MDS_ROW                                              \
   { 17u, 15u, 41u, 16u, 2u, 28u, 13u, 13u, 39u, 18u, 34u, 20u }
 
-// 128-bit (w3:w2:w1:w0) -> lazy 64-bit, carry-chain form (13 integer ops, no compares/selects).
-// NOTE on flags: `subc m,0,0` right after a SUB chain yields the borrow mask, but after an ADD chain
-// ptxas feeds the raw hardware carry into it (inverted meaning), so carries are materialised with
-// addc + neg instead.
-//   t = (w1:w0) - w3, minus EPS on borrow;  u = w2*(2^32-1) = (w2<<32) - w2;  r = t + u, plus EPS on carry.
-__device__ __forceinline__ u64 gl_reduce128_cc(u64 lo, u64 hi) {
-  u32 w0 = (u32)lo, w1 = (u32)(lo >> 32), w2 = (u32)hi, w3 = (u32)(hi >> 32), r0, r1;
-  asm("{\n\t.reg .u32 m,t0,t1,u0,u1;\n\t"
-      "sub.cc.u32 t0,%2,%5;\n\tsubc.cc.u32 t1,%3,0;\n\tsubc.u32 m,0,0;\n\t"
-      "sub.cc.u32 t0,t0,m;\n\tsubc.u32 t1,t1,0;\n\t"
-      "sub.cc.u32 u0,0,%4;\n\tsubc.u32 u1,%4,0;\n\t"
-      "add.cc.u32 t0,t0,u0;\n\taddc.cc.u32 t1,t1,u1;\n\taddc.u32 m,0,0;\n\tneg.s32 m,m;\n\t"
-      "add.cc.u32 %0,t0,m;\n\taddc.u32 %1,t1,0;\n\t}"
-      : "=r"(r0), "=r"(r1)
-      : "r"(w0), "r"(w1), "r"(w2), "r"(w3));
-  return ((u64)r1 << 32) | r0;
-}
-__device__ __forceinline__ u64 gl_mul_cc(u64 a, u64 b) {
-  // one 128-bit product: ptxas shares the partial products between the low and the high half
-  unsigned __int128 m = (unsigned __int128)a * b;
-  return gl_reduce128_cc((u64)m, (u64)(m >> 64));
-}
-
 // x^7 with 2 squarings + 2 multiplications (sbox1, Hash/Poseidon.hs:79-80)
 __device__ __forceinline__ u64 poseidon_sbox(u64 x) {
-  u64 x2 = gl_mul_cc(x, x);
-  u64 x3 = gl_mul_cc(x, x2);
-  u64 x4 = gl_mul_cc(x2, x2);
-  return gl_mul_cc(x3, x4);
+  u64 x2 = gl_mul(x, x);
+  u64 x3 = gl_mul(x, x2);
+  u64 x4 = gl_mul(x2, x2);
+  return gl_mul(x3, x4);
 }
 
 // s <- rc_next + MDS * s on 22/22/20-bit limbs.  Bounds: limb < 2^22, row sum of the coefficients
