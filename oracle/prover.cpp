@@ -20,9 +20,10 @@
 // The transcript uses oracle/challenger.hpp (shared with the verifier restatement; the Python
 // twin oracle/pyref.py re-derives the challenges independently).
 //
-//   p2v_prover <preset> <out_prefix> [--seed K] [--corrupt-layer S] [--bad-final] [--blob]
+//   p2v_prover <preset> <out_prefix> [--seed K] [--corrupt-layer S] [--bad-final] [--bad-witness ROW]
 //
-// Presets: s12 (standard recursion shape), mid5, small6, fixed4, lookup6.
+// Presets: s12 (standard recursion shape), mid5, small6, fixed4, lookup6 (all-Noop rows, quotient == 0);
+//          real5, real7 (ACTIVE gates of all 14 standard kinds on honest witnesses, real quotient C/Z_H).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -135,6 +136,7 @@ struct Preset {
   std::vector<Range> groups;
   int num_lookup_polys = 0;
   std::vector<std::vector<std::pair<u64, u64>>> luts;
+  bool real = false;  // rows with ACTIVE gates on honest witnesses + a real quotient polynomial
 };
 
 static const char *PHANTOM = "PhantomData<plonky2_field::goldilocks_field::GoldilocksField>";
@@ -218,6 +220,18 @@ static Preset makePreset(const std::string &name) {
     p.gates = {gNoop(), gConst(2), gPI(), gBaseSum(63, 2), gRedExt(32), gRed(43), gArithExt(10), gArith(20), gMulExt(13),
                gExp(66), gRA(4, 4, 2), gCoset(4, 6), gPoseidon(), gPoseidonMds()};
     assignGroups(p, {6, 5, 3});
+  } else if (name == "real5" || name == "real7") {
+    // Same gate set as the standard recursion shape, but the rows carry ACTIVE gates on honestly generated
+    // witnesses and the quotient polynomial is the real C(X)/Z_H(X).  Selector groups obey Plonky2's degree rule
+    // (group size + gate degree <= quotient_degree_factor + 1): {deg<=2} {deg<=4} {RandomAccess, CosetInterp} {Poseidon, PoseidonMds}.
+    p.real = true;
+    p.degree_bits = name == "real5" ? 5 : 7;
+    p.rate_bits = 3; p.cap_height = 2; p.pow_bits = 6; p.num_queries = 6;
+    p.arity_bits = 2; p.final_poly_bits = 2;
+    p.num_wires = 135; p.num_routed = 80; p.num_public_inputs = 5;
+    p.gates = {gNoop(), gConst(2), gPI(), gBaseSum(63, 2), gRedExt(32), gRed(43), gArithExt(10), gArith(20), gMulExt(13),
+               gExp(66), gRA(4, 4, 2), gCoset(4, 6), gPoseidon(), gPoseidonMds()};
+    assignGroups(p, {6, 4, 2, 2});
   } else if (name == "small6") {
     p.degree_bits = 6; p.rate_bits = 3; p.cap_height = 1; p.pow_bits = 8; p.num_queries = 5;
     p.arity_bits = 2; p.final_poly_bits = 3;
@@ -280,10 +294,172 @@ static CommonCircuitData toCommon(const Preset &p) {
   return c;
 }
 
+// ---- honest witness rows for ACTIVE gates (real circuits) --------------------------------------------------------
+// Each generator fills the wires a gate constrains from what the gate MEANS; unused wires stay random.
+static FExt EX(const std::vector<F> &w, int i) { return FExt(w[i], w[i + 1]); }
+static void putE(std::vector<F> &w, int i, const FExt &v) { w[i] = v.r; w[i + 1] = v.i; }
+
+static void witnessRow(const Gate &g, std::vector<F> &w, F c0, F c1, const Digest &pih, SplitMix &rng) {
+  switch (g.kind) {
+    case P2V_GATE_ARITHMETIC:
+      for (int i = 0; i < g.p0; i++) { int j = 4 * i; w[j + 3] = c0 * w[j] * w[j + 1] + c1 * w[j + 2]; }
+      break;
+    case P2V_GATE_ARITHMETIC_EXT:
+      for (int i = 0; i < g.p0; i++) { int j = 8 * i; putE(w, j + 6, scaleExt(c0, EX(w, j) * EX(w, j + 2)) + scaleExt(c1, EX(w, j + 4))); }
+      break;
+    case P2V_GATE_MUL_EXT:
+      for (int i = 0; i < g.p0; i++) { int j = 6 * i; putE(w, j + 4, scaleExt(c0, EX(w, j) * EX(w, j + 2))); }
+      break;
+    case P2V_GATE_BASE_SUM: {
+      F acc(0), pw(1);
+      for (int i = 0; i < g.p0; i++) {
+        u64 limb = rng.next() % (u64)g.p1;
+        w[1 + i] = F(limb);
+        acc = acc + F(limb) * pw;
+        pw = pw * F((u64)g.p1);
+      }
+      w[0] = acc;
+      break;
+    }
+    case P2V_GATE_CONSTANT:
+      if (g.p0 > 0) w[0] = c0;
+      if (g.p0 > 1) w[1] = c1;
+      break;
+    case P2V_GATE_PUBLIC_INPUT:
+      for (int i = 0; i < 4; i++) w[i] = pih.e[i];
+      break;
+    case P2V_GATE_EXPONENTIATION: {
+      int n = g.p0;
+      F base = w[0], acc(1);
+      std::vector<int> bits(n);
+      for (int i = 0; i < n; i++) { bits[i] = (int)(rng.next() & 1); w[1 + i] = F((u64)bits[i]); }
+      for (int i = 0; i < n; i++) {
+        int cur = bits[n - 1 - i];
+        acc = (i ? acc * acc : F(1)) * (cur ? base : F(1));
+        w[n + 2 + i] = acc;
+      }
+      w[n + 1] = acc;
+      break;
+    }
+    case P2V_GATE_REDUCING: case P2V_GATE_REDUCING_EXT: {
+      int n = g.p0;
+      bool ext = g.kind == P2V_GATE_REDUCING_EXT;
+      FExt alpha = EX(w, 2), acc = EX(w, 4);
+      for (int i = 0; i < n; i++) {
+        FExt coeff = ext ? EX(w, 6 + 2 * i) : fromBase(w[6 + i]);
+        acc = acc * alpha + coeff;
+        putE(w, i < n - 1 ? 6 + (ext ? 2 * n : n) + 2 * i : 0, acc);
+      }
+      break;
+    }
+    case P2V_GATE_RANDOM_ACCESS: {
+      int nb = g.p0, copies = g.p1, extra = g.p2, width = 2 + (1 << nb), start = width * copies + extra;
+      for (int k = 0; k < copies; k++) {
+        int idx = (int)(rng.next() % (u64)(1 << nb));
+        w[k * width] = F((u64)idx);
+        w[k * width + 1] = w[k * width + 2 + idx];
+        for (int j = 0; j < nb; j++) w[start + k * nb + j] = F((u64)((idx >> j) & 1));
+      }
+      if (extra > 0) w[copies * width] = c0;
+      if (extra > 1) w[copies * width + 1] = c1;
+      break;
+    }
+    case P2V_GATE_COSET_INTERP: {
+      int npts = 1 << g.p0, degree = g.p1, nint = (npts - 2) / (degree - 1), base = 1 + 2 * (npts + 2);
+      std::vector<F> dom = enumerateSubgroup(g.p0);
+      F shift = w[0];
+      FExt x0 = EX(w, base + 4 * nint);
+      putE(w, 1 + 2 * npts, scaleExt(shift, x0));
+      FExt ev = FE0(), pr = FE1();
+      int idx = 0, ck = 0;
+      while (idx < npts) {
+        int len = ck == 0 ? degree : degree - 1;
+        for (int k = 0; k < len && idx < npts; k++, idx++) {
+          FExt val = scaleExt(g.weights[idx], EX(w, 1 + 2 * idx));
+          FExt term = x0 - fromBase(dom[idx]);
+          FExt ne = term * ev + val * pr;
+          pr = term * pr;
+          ev = ne;
+        }
+        if (idx < npts) { putE(w, base + 2 * ck, ev); putE(w, base + 2 * (nint + ck), pr); }
+        ck++;
+      }
+      putE(w, 1 + 2 * npts + 2, ev);
+      break;
+    }
+    case P2V_GATE_POSEIDON_MDS:
+      for (int i = 0; i < 12; i++) {
+        FExt acc = FE0();
+        for (int j = 0; j < 12; j++) acc = acc + scaleExt(mdsMatrixCoeff(i, j), EX(w, 2 * j));
+        putE(w, 2 * (i + 12), acc);
+      }
+      break;
+    case P2V_GATE_POSEIDON: {
+      F swap((u64)(rng.next() & 1));
+      w[24] = swap;
+      F st[12];
+      for (int i = 0; i < 4; i++) {
+        F delta = swap * (w[i + 4] - w[i]);
+        w[25 + i] = delta;
+        st[i] = w[i] + delta;
+        st[i + 4] = w[i + 4] - delta;
+        st[i + 8] = w[i + 8];
+      }
+      State in;
+      for (int i = 0; i < 12; i++) in[i] = st[i];
+      auto mds = [&](F *s) { F o[12]; for (int i = 0; i < 12; i++) { F a(0); for (int j = 0; j < 12; j++) a = a + mdsMatrixCoeff(i, j) * s[j]; o[i] = a; } for (int i = 0; i < 12; i++) s[i] = o[i]; };
+      for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 12; i++) st[i] = st[i] + F(ALL_ROUND_CONSTANTS[r][i]);
+        if (r) for (int i = 0; i < 12; i++) w[29 + 12 * (r - 1) + i] = st[i];
+        for (int i = 0; i < 12; i++) st[i] = sbox1(st[i]);
+        mds(st);
+      }
+      for (int i = 0; i < 12; i++) st[i] = st[i] + F(FAST_PARTIAL_FIRST_RC[i]);
+      {
+        F t[12];
+        t[0] = st[0];
+        for (int i = 0; i < 11; i++) { F a(0); for (int j = 0; j < 11; j++) a = a + partialMdsMatrixCoeff(i, j) * st[j + 1]; t[i + 1] = a; }
+        for (int i = 0; i < 12; i++) st[i] = t[i];
+      }
+      for (int r = 0; r < 22; r++) {
+        w[65 + r] = st[0];
+        F y = sbox1(st[0]);
+        if (r < 21) y = y + F(FAST_PARTIAL_RCS[r]);
+        F d = y * mdsMatrixCoeff(0, 0);
+        for (int i = 0; i < 11; i++) d = d + st[i + 1] * F(FAST_PARTIAL_W_HATS[r][i]);
+        for (int i = 0; i < 11; i++) st[i + 1] = st[i + 1] + y * F(FAST_PARTIAL_VS[r][i]);
+        st[0] = d;
+      }
+      for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 12; i++) st[i] = st[i] + F(ALL_ROUND_CONSTANTS[26 + r][i]);
+        for (int i = 0; i < 12; i++) w[87 + 12 * r + i] = st[i];
+        for (int i = 0; i < 12; i++) st[i] = sbox1(st[i]);
+        mds(st);
+      }
+      for (int i = 0; i < 12; i++) w[12 + i] = st[i];
+      State out = permutation(in);
+      for (int i = 0; i < 12; i++)
+        if (out[i] != st[i]) { fprintf(stderr, "PoseidonGate witness != permutation\n"); exit(5); }
+      break;
+    }
+    default: break;  // Noop, Lookup*
+  }
+}
+
+// inverse NTT on the subgroup of size 2^logn (natural order): values -> coefficients
+static std::vector<F> intt(std::vector<F> v, int logn) {
+  size_t n = (size_t)1 << logn;
+  ntt(v, logn);
+  std::vector<F> out(n);
+  F ninv = inv(F((u64)n));
+  for (size_t k = 0; k < n; k++) out[k] = v[(n - k) % n] * ninv;
+  return out;
+}
+
 // ---- the prover ---------------------------------------------------------------------------------------
 struct ProverOut { VerifierOnlyCircuitData vk; ProofWithPublicInputs pw; };
 
-static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, int corrupt_layer, bool bad_final, int threads) {
+static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, int corrupt_layer, bool bad_final, int threads, int bad_witness_row = -1) {
   SplitMix rng(seed);
   int n = c.degree_bits, N = 1 << n, loglde = c.lde_bits(), M = 1 << loglde;
   int r = c.num_challenges;
@@ -294,52 +470,73 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
   if (noop_index < 0) { fprintf(stderr, "preset needs a NoopGate\n"); exit(2); }
   // --- column polynomials (coefficient form, degree < N) ---
   std::vector<std::vector<F>> const_cols, wire_cols, pp_cols, quot_cols;
-  for (size_t g = 0; g < c.selector_groups.size(); g++) {
-    F v = (int)g == c.selector_indices[noop_index] ? F::fromInt(noop_index) : F((u64)0xFFFFFFFFULL);
-    const_cols.push_back({v});
+  ProverOut out;
+  Digest pih;
+  if (p.real) {
+    // rows carry ACTIVE gates (round-robin over the gate list), honest witnesses, per-row gate constants
+    SplitMix rpi(seed ^ 0x5EEDF00DULL);
+    for (int i = 0; i < c.num_public_inputs; i++) out.pw.public_inputs.push_back(rpi.felt());
+    pih = sponge(out.pw.public_inputs);
+    int G = (int)c.gates.size(), ngrp = (int)c.selector_groups.size();
+    std::vector<std::vector<F>> cvals(ngrp + 2, std::vector<F>(N)), wvals(c.num_wires, std::vector<F>(N));
+    for (int row = 0; row < N; row++) {
+      int gi = row % G;
+      for (int g = 0; g < ngrp; g++) cvals[g][row] = g == c.selector_indices[gi] ? F::fromInt(gi) : F((u64)0xFFFFFFFFULL);
+      F c0 = rng.felt(), c1 = rng.felt();
+      cvals[ngrp][row] = c0; cvals[ngrp + 1][row] = c1;
+      std::vector<F> w(c.num_wires);
+      for (auto &x : w) x = rng.felt();
+      if (row != bad_witness_row) witnessRow(c.gates[gi], w, c0, c1, pih, rng);  // --bad-witness: leave that row's gate unsatisfied
+      for (int i = 0; i < c.num_wires; i++) wvals[i][row] = w[i];
+    }
+    for (auto &col : cvals) const_cols.push_back(intt(col, n));
+    for (auto &col : wvals) wire_cols.push_back(intt(col, n));
+  } else {
+    for (size_t g = 0; g < c.selector_groups.size(); g++) {
+      F v = (int)g == c.selector_indices[noop_index] ? F::fromInt(noop_index) : F((u64)0xFFFFFFFFULL);
+      const_cols.push_back({v});
+    }
+    for (int i = 0; i < c.num_lookup_selectors; i++) const_cols.push_back({F(0)});
+    for (int i = 0; i < 2; i++) const_cols.push_back({rng.felt()});      // gate constants
   }
-  for (int i = 0; i < c.num_lookup_selectors; i++) const_cols.push_back({F(0)});
-  for (int i = 0; i < 2; i++) const_cols.push_back({rng.felt()});      // gate constants
   for (int i = 0; i < c.num_routed_wires; i++) const_cols.push_back({F(0), c.k_is[i]});  // sigma_i(x) = k_i x
-  for (int i = 0; i < c.num_wires; i++) {
-    std::vector<F> co(N);
-    for (auto &x : co) x = rng.felt();
-    wire_cols.push_back(co);
-  }
+  if (!p.real)
+    for (int i = 0; i < c.num_wires; i++) {
+      std::vector<F> co(N);
+      for (auto &x : co) x = rng.felt();
+      wire_cols.push_back(co);
+    }
   for (int i = 0; i < r * (1 + c.num_partial_products); i++) pp_cols.push_back({F(1)});  // Z and partial products == 1
   for (int i = 0; i < r * c.num_lookup_polys; i++) {  // lookup columns: arbitrary low-degree
     std::vector<F> co(N);
     for (auto &x : co) x = rng.felt();
     pp_cols.push_back(co);
   }
-  for (int i = 0; i < r * c.quotient_degree_factor; i++) quot_cols.push_back({F(0)});  // quotient == 0
+  for (int i = 0; i < r * c.quotient_degree_factor; i++) quot_cols.push_back({F(0)});  // quotient == 0 unless p.real (below)
   std::vector<std::vector<std::vector<F>> *> mats = {&const_cols, &wire_cols, &pp_cols, &quot_cols};
 
   // --- LDE + commit: rows at x_i = g*eta^i, leaf j = row rev(j) ---
   auto t0 = std::chrono::steady_clock::now();
   std::vector<std::vector<std::vector<F>>> lde(4);  // [oracle][col][i]
-  for (int o = 0; o < 4; o++) {
-    lde[o].resize(mats[o]->size());
+  std::vector<Tree> trees(4);
+  auto commitOracle = [&](int o) {
+    lde[o].assign(mats[o]->size(), {});
     std::vector<std::thread> th;
     for (int k = 0; k < threads; k++)
       th.emplace_back([&, k, o]() {
         for (size_t col = k; col < mats[o]->size(); col += threads) lde[o][col] = ldeCoset((*mats[o])[col], loglde);
       });
     for (auto &x : th) x.join();
-  }
-  std::vector<Tree> trees;
-  for (int o = 0; o < 4; o++) {
     std::vector<std::vector<F>> leaves(M);
     for (int j = 0; j < M; j++) {
       int i = reverseBitsInt(loglde, j);
       leaves[j].resize(lde[o].size());
       for (size_t col = 0; col < lde[o].size(); col++) leaves[j][col] = lde[o][col][i];
     }
-    trees.push_back(buildTree(std::move(leaves), ncap_h, threads));
-  }
-  fprintf(stderr, "[prover] LDE + 4 trees: %.1fs\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    trees[o] = buildTree(std::move(leaves), ncap_h, threads);
+  };
+  for (int o = 0; o < 3; o++) commitOracle(o);
 
-  ProverOut out;
   out.vk.constants_sigmas_cap = trees[0].cap();
   {  // circuit digest: any 4 field elements (the reference only absorbs it, Challenge/Verifier.hs:73)
     std::vector<F> d;
@@ -348,20 +545,71 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
     out.vk.circuit_digest = sponge(d);
   }
   Proof &proof = out.pw.proof;
-  for (int i = 0; i < c.num_public_inputs; i++) out.pw.public_inputs.push_back(rng.felt());
+  if (!p.real)
+    for (int i = 0; i < c.num_public_inputs; i++) out.pw.public_inputs.push_back(rng.felt());
   proof.wires_cap = trees[1].cap();
   proof.plonk_zs_partial_products_cap = trees[2].cap();
-  proof.quotient_polys_cap = trees[3].cap();
 
-  // --- transcript up to zeta (Challenge/Verifier.hs:73-92) ---
+  // --- transcript up to the alphas (Challenge/Verifier.hs:73-88) ---
   Duplex dx(zeroState());
   dx.absorb(out.vk.circuit_digest);
   dx.absorb(sponge(out.pw.public_inputs));
   dx.absorb(proof.wires_cap);
-  dx.squeezeN(r); dx.squeezeN(r);
+  ProofChallenges pch;
+  pch.plonk_betas = dx.squeezeN(r);
+  pch.plonk_gammas = dx.squeezeN(r);
   if (c.num_lookup_polys > 0) dx.squeezeN(2 * r);
   dx.absorb(proof.plonk_zs_partial_products_cap);
-  dx.squeezeN(r);
+  pch.plonk_alphas = dx.squeezeN(r);
+
+  if (p.real) {
+    // --- the real quotient: t_j = C_j / Z_H on the LDE coset (deg C_j < 9N by the selector-group degree rule,
+    //     so deg t_j < 8N = M and its M coset values determine it), split into qdf chunks of N coefficients
+    //     (Plonk/Verifier.hs:44-47 reassembles sum_k zeta^{kN} chunk_k).  C_j(x) is evaluated with the SAME
+    //     function the verifier uses at zeta (evalCombinedPlonkConstraints), fed with the column values at x.
+    if (M != N * c.quotient_degree_factor) { fprintf(stderr, "real preset needs 2^rate_bits == quotient_degree_factor\n"); exit(2); }
+    std::vector<std::vector<F>> tvals(r, std::vector<F>(M));
+    F eta = subgroupGenerator(loglde);
+    std::vector<F> xs(M);
+    { F x(MUL_GEN); for (int i = 0; i < M; i++) { xs[i] = x; x = x * eta; } }
+    std::vector<std::thread> th;
+    for (int k = 0; k < threads; k++)
+      th.emplace_back([&, k]() {
+        for (int i = k; i < M; i += threads) {
+          ProofWithPublicInputs fake;
+          fake.public_inputs = out.pw.public_inputs;
+          OpeningSet &fo = fake.proof.openings;
+          for (int t = 0; t < c.num_constants; t++) fo.constants.push_back(fromBase(lde[0][t][i]));
+          for (size_t t = c.num_constants; t < lde[0].size(); t++) fo.plonk_sigmas.push_back(fromBase(lde[0][t][i]));
+          for (auto &col : lde[1]) fo.wires.push_back(fromBase(col[i]));
+          fo.plonk_zs.assign(r, FE1());
+          fo.plonk_zs_next.assign(r, FE1());
+          fo.partial_products.assign(r * c.num_partial_products, FE1());
+          ProofChallenges ch = pch;
+          ch.plonk_zeta = fromBase(xs[i]);
+          std::vector<FExt> cj = evalCombinedPlonkConstraints(c, fake, ch);
+          F zh = inv(powu(xs[i], (u64)N) - F(1));
+          for (int j = 0; j < r; j++) {
+            if (cj[j].i != F(0)) { fprintf(stderr, "[prover] constraint value left the base field\n"); exit(6); }
+            tvals[j][i] = cj[j].r * zh;
+          }
+        }
+      });
+    for (auto &x : th) x.join();
+    quot_cols.clear();
+    F ginv = inv(F(MUL_GEN));
+    for (int j = 0; j < r; j++) {
+      std::vector<F> co = intt(tvals[j], loglde);
+      F gp(1);
+      for (auto &x : co) { x = x * gp; gp = gp * ginv; }
+      for (int k = 0; k < c.quotient_degree_factor; k++) quot_cols.push_back(std::vector<F>(co.begin() + (size_t)k * N, co.begin() + (size_t)(k + 1) * N));
+    }
+    // sanity: on every row of H the combined constraint must vanish, i.e. t_j is a polynomial (checked through the
+    // verifier's identity at zeta by the caller's self-check; here: C_j at the first rows of H)
+  }
+  commitOracle(3);
+  proof.quotient_polys_cap = trees[3].cap();
+  fprintf(stderr, "[prover] LDE + 4 trees: %.1fs\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   dx.absorb(proof.quotient_polys_cap);
   FExt zeta = dx.squeezeExt();
   FExt omega_zeta = fromBase(subgroupGenerator(n)) * zeta;
@@ -611,18 +859,19 @@ static std::string proofJson(const ProofWithPublicInputs &pw) {
 
 int main(int argc, char **argv) {
   if (argc < 3) {
-    fprintf(stderr, "usage: p2v_prover <preset> <out_prefix> [--seed K] [--corrupt-layer S] [--bad-final] [--threads T]\n");
+    fprintf(stderr, "usage: p2v_prover <preset> <out_prefix> [--seed K] [--corrupt-layer S] [--bad-final] [--bad-witness ROW] [--threads T]\n");
     return 2;
   }
   std::string preset = argv[1], prefix = argv[2];
   u64 seed = 1;
-  int corrupt_layer = -1, threads = (int)std::thread::hardware_concurrency();
+  int corrupt_layer = -1, bad_witness_row = -1, threads = (int)std::thread::hardware_concurrency();
   bool bad_final = false;
   for (int i = 3; i < argc; i++) {
     std::string a = argv[i];
     if (a == "--seed" && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 10);
     else if (a == "--corrupt-layer" && i + 1 < argc) corrupt_layer = atoi(argv[++i]);
     else if (a == "--bad-final") bad_final = true;
+    else if (a == "--bad-witness" && i + 1 < argc) bad_witness_row = atoi(argv[++i]);
     else if (a == "--threads" && i + 1 < argc) threads = atoi(argv[++i]);
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
   }
@@ -630,7 +879,7 @@ int main(int argc, char **argv) {
   activePermutation() = permutationBulk;  // bit-identical to `permutation` (tests/test_oracle.py)
   Preset p = makePreset(preset);
   CommonCircuitData c = toCommon(p);
-  ProverOut out = prove(p, c, seed, corrupt_layer, bad_final, threads);
+  ProverOut out = prove(p, c, seed, corrupt_layer, bad_final, threads, bad_witness_row);
   // self-check with the verifier restatement (dense-MDS permutation)
   activePermutation() = permutation;
   permCounter() = 0;

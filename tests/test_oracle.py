@@ -109,7 +109,10 @@ def test_bundled_fixtures_accept(orc, name):
     res = orc.verify_batch(shape, vkey, blob, threads=1, fast=(name == "s12"))
     assert res["status"][0] == 0
     assert res["eqmask"][0] == (1 << shape.num_challenges) - 1
-    assert not res["combined"].any()  # the trivial circuit: every combined constraint value is 0
+    if name.startswith("real"):
+        assert res["combined"].any()      # active gates: C_j(zeta) != 0 and equals Z_H(zeta) * quotient(zeta)
+    else:
+        assert not res["combined"].any()  # the trivial circuit: every combined constraint value is 0
     assert (res["qstatus"] == 0).all()
     assert orc.blob_words(shape, blob) == lay.blob_words
 
@@ -122,7 +125,8 @@ def test_s12_permutation_count(orc):
     assert res["perms"] == 2774 + 2
 
 
-@pytest.mark.parametrize("name,code", [("small6_badfinal", 3), ("small6_badlayer0", 18), ("small6_badlayer1", 18 | (1 << 16))])
+@pytest.mark.parametrize("name,code", [("small6_badfinal", 3), ("small6_badlayer0", 18), ("small6_badlayer1", 18 | (1 << 16)),
+                                       ("real5_badwitness", 1 | (3 << 16))])
 def test_regrinded_rejections(orc, name, code):
     shape, lay, vkey, blob = fixtures.load(name)
     res = orc.verify_batch(shape, vkey, blob, threads=1, fast=False)
