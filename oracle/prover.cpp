@@ -2,11 +2,14 @@
 //
 // The reference ships no fixtures (its json/ directory is git-ignored, .gitignore:4,6; testmain
 // reads ../json/<prefix>_{common,vkey,proof}.json, src/testmain.hs:25-33) and no prover.  This is
-// the trivial-circuit mini-prover of SURVEY.md App. F: it produces ACCEPTING Plonky2 proofs of a
+// the mini-prover of SURVEY.md App. F (extended to real circuits): it produces ACCEPTING Plonky2 proofs of a
 // chosen circuit SHAPE (gate list, widths, FRI parameters) in the reference's JSON wire format
 // (src/Types.hs aeson instances), so that `testmain` could consume them unchanged.
 //
-// Circuit: every row is a NoopGate, the wiring permutation is the identity.
+// Real presets (real5, real7): every row carries an ACTIVE gate on an honest witness, Noop rows are wired to the
+// active rows by copy constraints (non-identity sigma, real grand product Z and partial products), and the
+// quotient polynomial is the real C(X)/Z_H(X) — see `witnessRow` and the p.real branches of `prove`.
+// Trivial presets: every row is a NoopGate, the wiring permutation is the identity.
 //   - selector column of Noop's group == index(Noop), other selector columns == UNUSED (2^32-1),
 //     lookup selectors == 0  =>  every gate filter (Gate/Selector.hs:83-89) and lookup equation
 //     vanishes identically;
@@ -20,7 +23,7 @@
 // The transcript uses oracle/challenger.hpp (shared with the verifier restatement; the Python
 // twin oracle/pyref.py re-derives the challenges independently).
 //
-//   p2v_prover <preset> <out_prefix> [--seed K] [--corrupt-layer S] [--bad-final] [--bad-witness ROW]
+//   p2v_prover <preset> <out_prefix> [--seed K] [--corrupt-layer S] [--bad-final] [--bad-witness ROW] [--bad-copy]
 //
 // Presets: s12 (standard recursion shape), mid5, small6, fixed4, lookup6 (all-Noop rows, quotient == 0);
 //          real5, real7 (ACTIVE gates of all 14 standard kinds on honest witnesses, real quotient C/Z_H).
@@ -459,7 +462,7 @@ static std::vector<F> intt(std::vector<F> v, int logn) {
 // ---- the prover ---------------------------------------------------------------------------------------
 struct ProverOut { VerifierOnlyCircuitData vk; ProofWithPublicInputs pw; };
 
-static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, int corrupt_layer, bool bad_final, int threads, int bad_witness_row = -1) {
+static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, int corrupt_layer, bool bad_final, int threads, int bad_witness_row = -1, bool bad_copy = false) {
   SplitMix rng(seed);
   int n = c.degree_bits, N = 1 << n, loglde = c.lde_bits(), M = 1 << loglde;
   int r = c.num_challenges;
@@ -470,6 +473,7 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
   if (noop_index < 0) { fprintf(stderr, "preset needs a NoopGate\n"); exit(2); }
   // --- column polynomials (coefficient form, degree < N) ---
   std::vector<std::vector<F>> const_cols, wire_cols, pp_cols, quot_cols;
+  std::vector<std::vector<F>> sigma_vals, real_wvals;  // real circuits: sigma and wire columns as values over H
   ProverOut out;
   Digest pih;
   if (p.real) {
@@ -489,6 +493,39 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
       if (row != bad_witness_row) witnessRow(c.gates[gi], w, c0, c1, pih, rng);  // --bad-witness: leave that row's gate unsatisfied
       for (int i = 0; i < c.num_wires; i++) wvals[i][row] = w[i];
     }
+    // copy constraints: the routed wires of the Noop rows (unconstrained by any gate) are wired to routed cells of
+    // the active rows and to each other, giving 2- and 3-cycles of the wiring permutation sigma
+    // (cell (row,col) <-> field element k_col * omega^row, Plonk/Vanishing.hs:96-111).
+    int R = c.num_routed_wires;
+    std::vector<int> sigma((size_t)N * R);
+    for (size_t i = 0; i < sigma.size(); i++) sigma[i] = (int)i;
+    auto cell = [&](int row, int col) { return row * R + col; };
+    auto joinCycle = [&](int a, int b) { sigma[a] = sigma[b]; sigma[b] = a; };  // a: singleton, joins b's cycle
+    {
+      std::vector<char> used((size_t)N * R, 0);
+      std::vector<int> noop_rows;
+      for (int row = 0; row < N; row++) if (row % G == noop_index) noop_rows.push_back(row);
+      for (size_t k = 0; k < noop_rows.size(); k++)
+        for (int col = 0; col < R; col++) {
+          int a = cell(noop_rows[k], col), b;
+          if (k > 0 && (col & 1)) b = cell(noop_rows[k - 1], (col * 7 + 3) % R);  // extend an existing cycle
+          else
+            do { b = cell((int)(rng.next() % (u64)N), (int)(rng.next() % (u64)R)); } while (used[b] || (b / R) % G == noop_index);
+          used[b] = 1;
+          wvals[col][noop_rows[k]] = wvals[b % R][b / R];
+          joinCycle(a, b);
+        }
+    }
+    if (bad_copy) wvals[0][noop_index] = wvals[0][noop_index] + F(1);  // --bad-copy: one wired cell no longer equals its cycle
+    sigma_vals.assign(R, std::vector<F>(N));
+    {
+      std::vector<F> wp(N);
+      F w1 = subgroupGenerator(n), x(1);
+      for (int i = 0; i < N; i++) { wp[i] = x; x = x * w1; }
+      for (int row = 0; row < N; row++)
+        for (int col = 0; col < R; col++) { int t = sigma[cell(row, col)]; sigma_vals[col][row] = c.k_is[t % R] * wp[t / R]; }
+    }
+    real_wvals = wvals;
     for (auto &col : cvals) const_cols.push_back(intt(col, n));
     for (auto &col : wvals) wire_cols.push_back(intt(col, n));
   } else {
@@ -499,7 +536,10 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
     for (int i = 0; i < c.num_lookup_selectors; i++) const_cols.push_back({F(0)});
     for (int i = 0; i < 2; i++) const_cols.push_back({rng.felt()});      // gate constants
   }
-  for (int i = 0; i < c.num_routed_wires; i++) const_cols.push_back({F(0), c.k_is[i]});  // sigma_i(x) = k_i x
+  for (int i = 0; i < c.num_routed_wires; i++) {
+    if (p.real) const_cols.push_back(intt(sigma_vals[i], n));
+    else const_cols.push_back({F(0), c.k_is[i]});  // identity wiring: sigma_i(x) = k_i x
+  }
   if (!p.real)
     for (int i = 0; i < c.num_wires; i++) {
       std::vector<F> co(N);
@@ -535,7 +575,7 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
     }
     trees[o] = buildTree(std::move(leaves), ncap_h, threads);
   };
-  for (int o = 0; o < 3; o++) commitOracle(o);
+  for (int o = 0; o < 2; o++) commitOracle(o);
 
   out.vk.constants_sigmas_cap = trees[0].cap();
   {  // circuit digest: any 4 field elements (the reference only absorbs it, Challenge/Verifier.hs:73)
@@ -548,7 +588,6 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
   if (!p.real)
     for (int i = 0; i < c.num_public_inputs; i++) out.pw.public_inputs.push_back(rng.felt());
   proof.wires_cap = trees[1].cap();
-  proof.plonk_zs_partial_products_cap = trees[2].cap();
 
   // --- transcript up to the alphas (Challenge/Verifier.hs:73-88) ---
   Duplex dx(zeroState());
@@ -559,6 +598,38 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
   pch.plonk_betas = dx.squeezeN(r);
   pch.plonk_gammas = dx.squeezeN(r);
   if (c.num_lookup_polys > 0) dx.squeezeN(2 * r);
+  if (p.real) {
+    // grand product Z and its partial products per challenge round (Plonk/Vanishing.hs:96-111):
+    // current = [Z, pp_0 .. pp_{m-1}, Z(omega x)],  current[t+1] = current[t] * numer_t / denom_t  with the routed
+    // wires taken in chunks of quotient_degree_factor.
+    int R = c.num_routed_wires, qd = c.quotient_degree_factor, npp = c.num_partial_products;
+    std::vector<std::vector<F>> zvals(r, std::vector<F>(N)), ppvals((size_t)r * npp, std::vector<F>(N));
+    F w1 = subgroupGenerator(n);
+    for (int j = 0; j < r; j++) {
+      F beta = pch.plonk_betas[j], gamma = pch.plonk_gammas[j], z(1), x(1);
+      for (int row = 0; row < N; row++) {
+        zvals[j][row] = z;
+        F cur = z;
+        for (int t = 0; t * qd < R; t++) {
+          F num(1), den(1);
+          for (int col = t * qd; col < std::min(R, (t + 1) * qd); col++) {
+            num = num * (real_wvals[col][row] + beta * c.k_is[col] * x + gamma);
+            den = den * (real_wvals[col][row] + beta * sigma_vals[col][row] + gamma);
+          }
+          cur = cur * num * inv(den);
+          if (t < npp) ppvals[(size_t)j * npp + t][row] = cur;
+        }
+        z = cur;
+        x = x * w1;
+      }
+      if (z != F(1) && !bad_copy) { fprintf(stderr, "[prover] grand product does not close: sigma is not value-preserving\n"); exit(7); }
+    }
+    pp_cols.clear();
+    for (auto &col : zvals) pp_cols.push_back(intt(col, n));
+    for (auto &col : ppvals) pp_cols.push_back(intt(col, n));
+  }
+  commitOracle(2);
+  proof.plonk_zs_partial_products_cap = trees[2].cap();
   dx.absorb(proof.plonk_zs_partial_products_cap);
   pch.plonk_alphas = dx.squeezeN(r);
 
@@ -582,9 +653,9 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
           for (int t = 0; t < c.num_constants; t++) fo.constants.push_back(fromBase(lde[0][t][i]));
           for (size_t t = c.num_constants; t < lde[0].size(); t++) fo.plonk_sigmas.push_back(fromBase(lde[0][t][i]));
           for (auto &col : lde[1]) fo.wires.push_back(fromBase(col[i]));
-          fo.plonk_zs.assign(r, FE1());
-          fo.plonk_zs_next.assign(r, FE1());
-          fo.partial_products.assign(r * c.num_partial_products, FE1());
+          int inext = (i + (M >> n)) % M;  // omega * x_i = x_{i + M/N}
+          for (int t = 0; t < r; t++) { fo.plonk_zs.push_back(fromBase(lde[2][t][i])); fo.plonk_zs_next.push_back(fromBase(lde[2][t][inext])); }
+          for (int t = 0; t < r * c.num_partial_products; t++) fo.partial_products.push_back(fromBase(lde[2][r + t][i]));
           ProofChallenges ch = pch;
           ch.plonk_zeta = fromBase(xs[i]);
           std::vector<FExt> cj = evalCombinedPlonkConstraints(c, fake, ch);
@@ -859,18 +930,19 @@ static std::string proofJson(const ProofWithPublicInputs &pw) {
 
 int main(int argc, char **argv) {
   if (argc < 3) {
-    fprintf(stderr, "usage: p2v_prover <preset> <out_prefix> [--seed K] [--corrupt-layer S] [--bad-final] [--bad-witness ROW] [--threads T]\n");
+    fprintf(stderr, "usage: p2v_prover <preset> <out_prefix> [--seed K] [--corrupt-layer S] [--bad-final] [--bad-witness ROW] [--bad-copy] [--threads T]\n");
     return 2;
   }
   std::string preset = argv[1], prefix = argv[2];
   u64 seed = 1;
   int corrupt_layer = -1, bad_witness_row = -1, threads = (int)std::thread::hardware_concurrency();
-  bool bad_final = false;
+  bool bad_final = false, bad_copy = false;
   for (int i = 3; i < argc; i++) {
     std::string a = argv[i];
     if (a == "--seed" && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 10);
     else if (a == "--corrupt-layer" && i + 1 < argc) corrupt_layer = atoi(argv[++i]);
     else if (a == "--bad-final") bad_final = true;
+    else if (a == "--bad-copy") bad_copy = true;
     else if (a == "--bad-witness" && i + 1 < argc) bad_witness_row = atoi(argv[++i]);
     else if (a == "--threads" && i + 1 < argc) threads = atoi(argv[++i]);
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
@@ -879,7 +951,7 @@ int main(int argc, char **argv) {
   activePermutation() = permutationBulk;  // bit-identical to `permutation` (tests/test_oracle.py)
   Preset p = makePreset(preset);
   CommonCircuitData c = toCommon(p);
-  ProverOut out = prove(p, c, seed, corrupt_layer, bad_final, threads, bad_witness_row);
+  ProverOut out = prove(p, c, seed, corrupt_layer, bad_final, threads, bad_witness_row, bad_copy);
   // self-check with the verifier restatement (dense-MDS permutation)
   activePermutation() = permutation;
   permCounter() = 0;

@@ -12,13 +12,15 @@ $P mid5    $G/mid5    --seed 2
 $P small6  $G/small6  --seed 3
 $P fixed4  $G/fixed4  --seed 4
 $P lookup6 $G/lookup6 --seed 5
-# real circuit: ACTIVE gates of all 14 standard kinds on honest witnesses, real quotient polynomial
+# real circuit: ACTIVE gates of all 14 standard kinds on honest witnesses, copy constraints (non-identity sigma,
+# real grand product Z + partial products), real quotient polynomial
 $P real5   $G/real5   --seed 6
 # rejecting proofs that need a prover-side change (re-grinding after the change):
 $P small6 $G/small6_badfinal  --seed 3 --bad-final        # -> FALSE_FINAL
 $P small6 $G/small6_badlayer0 --seed 3 --corrupt-layer 0  # -> ERR_STEP_EVAL(step 0)
 $P small6 $G/small6_badlayer1 --seed 3 --corrupt-layer 1  # -> ERR_STEP_EVAL(step 1)
 $P real5  $G/real5_badwitness  --seed 6 --bad-witness 12  # PoseidonGate row left unsatisfied -> FALSE_EQS
-rm -f $G/real5_badwitness_common.json
+$P real5  $G/real5_badcopy     --seed 6 --bad-copy        # one wired cell differs from its cycle -> FALSE_EQS
+rm -f $G/real5_badwitness_common.json $G/real5_badcopy_common.json
 # the variants share small6's circuit: keep one copy of common/vkey where identical
 for v in badfinal badlayer0 badlayer1; do rm -f $G/small6_${v}_common.json; done
