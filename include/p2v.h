@@ -234,6 +234,14 @@ int p2v_parse_vkey(const char *json, size_t len, const p2v_shape *shape, uint64_
 /* `FromJSON ProofWithPublicInputs`: out[blob_words]; P2V_E_SHAPE when a list length differs
  * from the circuit's shape (the `error`s of safeZip, buildListOracle and validateMerkleCapLength in the reference). */
 int p2v_parse_proof(const char *json, size_t len, const p2v_shape *shape, uint64_t *out);
+/* The same for a batch (`mapM decodeProof` over the files testmain would read one by one, src/testmain.hs:33):
+ * proof i = jsons[i][0..lens[i]) -> blobs[i * blob_words ..], decoded on `threads` host threads (<= 0: all
+ * hardware threads).  rcs (may be NULL) receives each proof's P2V_OK / P2V_E_PARSE / P2V_E_SHAPE; a proof that
+ * fails to decode leaves its blob zeroed and does NOT stop the others.  Returns P2V_OK when every proof decoded,
+ * else the error code of the first failing proof (its message in p2v_last_error(NULL)).  blobs may be pinned
+ * memory from p2v_host_alloc, so that p2v_verify_batch copies straight from it. */
+int p2v_parse_proofs(const char *const *jsons, const size_t *lens, size_t n, const p2v_shape *shape, uint64_t *blobs,
+                     int threads, int32_t *rcs);
 
 /* ---- circuits and batches ------------------------------------------------------ */
 /* VerifierCircuitData (Types.hs: verifier_only + verifier_common) resident on the GPU. */

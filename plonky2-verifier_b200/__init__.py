@@ -130,6 +130,7 @@ def lib():
         "p2v_challenges_words": (C.c_int, [C.POINTER(Shape)]),
         "p2v_parse_vkey": (C.c_int, [C.c_char_p, sz, C.POINTER(Shape), u64p]),
         "p2v_parse_proof": (C.c_int, [C.c_char_p, sz, C.POINTER(Shape), u64p]),
+        "p2v_parse_proofs": (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(sz), sz, C.POINTER(Shape), u64p, C.c_int, C.c_void_p]),
         "p2v_circuit_create": (C.c_int, [vp, C.POINTER(Shape), u64p, C.POINTER(vp)]),
         "p2v_circuit_destroy": (None, [vp]),
         "p2v_challenges": (C.c_int, [vp, vp, u64p, sz, u64p]),
@@ -155,7 +156,7 @@ EXPORTED_SYMBOLS = [
     "p2v_ctx_launch_count", "p2v_host_alloc", "p2v_host_free", "p2v_poseidon_permute", "p2v_hash_leaves",
     "p2v_compress", "p2v_merkle_verify", "p2v_merkle_build", "p2v_merkle_open", "p2v_parse_common",
     "p2v_shape_free", "p2v_parse_gate", "p2v_shape_layout", "p2v_challenges_words", "p2v_parse_vkey",
-    "p2v_parse_proof", "p2v_circuit_create", "p2v_circuit_destroy", "p2v_challenges", "p2v_constraints",
+    "p2v_parse_proof", "p2v_parse_proofs", "p2v_circuit_create", "p2v_circuit_destroy", "p2v_challenges", "p2v_constraints",
     "p2v_fri", "p2v_verify_batch", "p2v_ctx_set_chunk", "p2v_ctx_set_pipeline", "p2v_synth_batch", "p2v_int_pipe_peak", "p2v_ctx_last_ms",
 ]
 
@@ -235,6 +236,27 @@ def parse_proof(json_text, shape):
     lay = shape_layout(shape)
     out = np.zeros(lay.blob_words, dtype=np.uint64)
     rc = lib().p2v_parse_proof(json_text, len(json_text), C.byref(shape), out.ctypes.data)
+    if rc:
+        raise P2VError(rc, lib().p2v_last_error(None).decode())
+    return out
+
+
+def parse_proofs(json_texts, shape, threads=0, out=None, return_codes=False):
+    """Decode a batch of `*_proof.json` texts on `threads` host threads (0 = all) -> u64 [n][blob_words].
+    `out` may be a (pinned) array to fill.  With return_codes=True a proof that fails to decode leaves a zero blob
+    and its error code in the second result instead of raising."""
+    texts = [t.encode() if isinstance(t, str) else t for t in json_texts]
+    n = len(texts)
+    lay = shape_layout(shape)
+    if out is None:
+        out = np.zeros((n, lay.blob_words), dtype=np.uint64)
+    assert out.dtype == np.uint64 and out.size >= n * lay.blob_words and out.flags.c_contiguous
+    ptrs = (C.c_char_p * n)(*texts)
+    lens = (C.c_size_t * n)(*[len(t) for t in texts])
+    rcs = np.zeros(n, dtype=np.int32)
+    rc = lib().p2v_parse_proofs(ptrs, lens, n, C.byref(shape), out.ctypes.data, int(threads), rcs.ctypes.data)
+    if return_codes:
+        return out, rcs
     if rc:
         raise P2VError(rc, lib().p2v_last_error(None).decode())
     return out

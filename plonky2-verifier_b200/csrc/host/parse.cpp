@@ -10,6 +10,10 @@
 #include <string>
 #include <vector>
 #include "../../../include/p2v.h"
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <thread>
 #include "json.hpp"
 
 using namespace p2vhost;
@@ -373,7 +377,8 @@ int p2v_parse_common(const char *json, size_t len, p2v_shape *out) {
   memset(out, 0, sizeof *out);
   uint64_t *luts = nullptr;
   try {
-    JValue root = JsonParser(json, len).parse();
+    JsonDoc doc(json, len);
+    JValue root = doc.root();
     const JValue &cfg = root.at("config");
     p2v_shape &s = *out;
     s.num_wires = (int)cfg.at("num_wires").integer();
@@ -412,9 +417,9 @@ int p2v_parse_common(const char *json, size_t len, p2v_shape *out) {
       return fail(P2V_E_UNSUPPORTED, "FRI parameters out of range");
     // expandReductionStrategy, Plonk/FRI.hs:337-354 (NOT fri_params.reduction_arity_bits)
     const JValue &strat = fc.at("reduction_strategy");
-    if (strat.kind != JValue::Object || strat.obj.size() != 1) throw JsonError("FriReductionStrategy: expecting a singleton object");
-    const std::string &key = strat.obj[0].first;
-    const JValue &sval = strat.obj[0].second;
+    if (!strat.isObject() || strat.objSize() != 1) throw JsonError("FriReductionStrategy: expecting a singleton object");
+    const std::string key = strat.objKey(0);
+    const JValue sval = strat.objVal(0);
     s.num_steps = 0;
     int total = 0;
     auto addStep = [&](int ar) {
@@ -525,7 +530,8 @@ int p2v_parse_common(const char *json, size_t len, p2v_shape *out) {
 int p2v_parse_vkey(const char *json, size_t len, const p2v_shape *shape, uint64_t *out) {
   if (!json || !shape || !out) return fail(P2V_E_INVALID, "p2v_parse_vkey: NULL argument");
   try {
-    JValue root = JsonParser(json, len).parse();
+    JsonDoc doc(json, len);
+    JValue root = doc.root();
     uint64_t *w = out;
     putCap(root.at("constants_sigmas_cap"), 1 << shape->cap_height, w, "constants_sigmas_cap");
     putDigest(root.at("circuit_digest"), w);
@@ -543,7 +549,8 @@ int p2v_parse_proof(const char *json, size_t len, const p2v_shape *shape, uint64
   int rc = layoutImpl(*shape, L);
   if (rc) return rc;
   try {
-    JValue root = JsonParser(json, len).parse();
+    JsonDoc doc(json, len);
+    JValue root = doc.root();
     const JValue &proof = root.at("proof");
     int ncap = 1 << shape->cap_height;
     uint64_t *w = out;
@@ -597,6 +604,41 @@ int p2v_parse_proof(const char *json, size_t len, const p2v_shape *shape, uint64
   } catch (const std::exception &e) {
     return fail(P2V_E_PARSE, std::string("p2v_parse_proof: ") + e.what());
   }
+  return P2V_OK;
+}
+
+int p2v_parse_proofs(const char *const *jsons, const size_t *lens, size_t n, const p2v_shape *shape, uint64_t *blobs,
+                     int threads, int32_t *rcs) {
+  if ((n && (!jsons || !lens || !blobs)) || !shape) return fail(P2V_E_INVALID, "p2v_parse_proofs: NULL argument");
+  p2v_layout L;
+  int rc = layoutImpl(*shape, L);
+  if (rc) return rc;
+  if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+  threads = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n));
+  std::atomic<size_t> next_item{0};
+  std::mutex mu;
+  size_t first_bad = n;
+  int first_rc = P2V_OK;
+  std::string first_msg;
+  auto work = [&]() {
+    for (;;) {
+      size_t i = next_item.fetch_add(1);
+      if (i >= n) return;
+      uint64_t *out = blobs + i * (size_t)L.blob_words;
+      int r = jsons[i] ? p2v_parse_proof(jsons[i], lens[i], shape, out) : fail(P2V_E_INVALID, "p2v_parse_proofs: NULL text");
+      if (rcs) rcs[i] = r;
+      if (r != P2V_OK) {
+        std::fill(out, out + L.blob_words, (uint64_t)0);
+        std::lock_guard<std::mutex> lk(mu);
+        if (i < first_bad) { first_bad = i; first_rc = r; first_msg = "proof " + std::to_string(i) + ": " + p2v_tls_error; }
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; t++) pool.emplace_back(work);
+  work();
+  for (auto &t : pool) t.join();
+  if (first_rc != P2V_OK) return fail(first_rc, first_msg);
   return P2V_OK;
 }
 

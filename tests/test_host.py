@@ -227,3 +227,45 @@ def test_shape_and_parse_errors(p2v):
     with pytest.raises(p2v.P2VError) as e:
         p2v.parse_common(json.dumps(c2))
     assert e.value.code == -5  # getSelectorConfig tally (Selector.hs:33-36)
+
+
+def test_number_tokens_of_any_length(p2v):
+    """`mkGoldilocks <$> parseJSON` (Goldilocks.hs:101-102,132-133): any non-negative integer, reduced mod p exactly —
+    19-, 20-, 38-, 39- and 60-digit tokens, values around p, 2^64 and 2^128, leading zeros are not JSON."""
+    shape, lay, vkey, blob = fixtures.load("small6")
+    proof = json.loads(fixtures.read("small6", "proof"))
+    rng = np.random.default_rng(5)
+    vals = [0, 1, P - 1, P, P + 1, 2**64 - 1, 2**64, 2**64 + 1, 10**19 - 1, 10**19, 10**38 - 1, 10**38, 2**128 - 1, 2**128, 2**128 + 12345,
+            10**59 + 7, 3 * P * P + 5]
+    vals += [int(rng.integers(0, 2**63)) ** k + int(rng.integers(0, 2**63)) for k in (1, 2, 3) for _ in range(20)]
+    txt = json.dumps(proof)
+    for v in vals:
+        p2 = json.loads(txt)
+        p2["proof"]["opening_proof"]["pow_witness"] = v
+        got = p2v.parse_proof(json.dumps(p2), shape)
+        assert int(got[lay.off_pow_witness]) == v % P, v
+
+
+def test_batch_parse_on_threads(p2v):
+    """p2v_parse_proofs == p2v_parse_proof on every text, for any thread count; a text that fails to decode is
+    reported per proof, leaves a zero blob and does not stop the others."""
+    shape, lay, vkey, blob = fixtures.load("small6")
+    good = fixtures.read("small6", "proof")
+    variants = [good, fixtures.read("small6_badfinal", "proof"), fixtures.read("small6_badlayer0", "proof")]
+    texts = [variants[i % 3] for i in range(37)]
+    want = np.stack([p2v.parse_proof(t, shape) for t in texts])
+    for threads in (1, 3, 0):
+        assert np.array_equal(p2v.parse_proofs(texts, shape, threads=threads), want)
+    bad = json.loads(good)
+    bad["proof"]["wires_cap"].pop()
+    texts[5] = json.dumps(bad)
+    texts[20] = "{ not json"
+    out, rcs = p2v.parse_proofs(texts, shape, threads=4, return_codes=True)
+    assert rcs[5] == -5 and rcs[20] == -4 and (np.delete(rcs, [5, 20]) == 0).all()
+    assert not out[5].any() and not out[20].any()
+    keep = [i for i in range(37) if i not in (5, 20)]
+    assert np.array_equal(out[keep], want[keep])
+    with pytest.raises(p2v.P2VError) as e:
+        p2v.parse_proofs(texts, shape, threads=4)
+    assert e.value.code == -5 and "proof 5" in str(e.value)
+    assert p2v.parse_proofs([], shape).shape == (0, lay.blob_words)
