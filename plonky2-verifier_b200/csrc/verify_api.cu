@@ -239,6 +239,10 @@ __global__ void k_lookup_delta_copies(DevCircuit c, Workspace ws, size_t n) {
     }
 }
 
+#ifndef P2V_RAMP_NUM
+#define P2V_RAMP_NUM 9
+#define P2V_RAMP_DEN 8
+#endif
 int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t n, int what, Outputs out) {
   if (!ctx || !cir || !blobs) return p2v_fail(ctx, P2V_E_INVALID, "NULL argument");
   if (cir->ctx != ctx) return p2v_fail(ctx, P2V_E_INVALID, "circuit belongs to another context");
@@ -286,12 +290,17 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   }
   const bool timed = depth == 1;
   int k = 0;
-  // host input on the pipeline: ramp the first chunks up (chunk/8, /4, /2, then full) so that the H2D copy that
-  // nothing can hide (the very first one) is short.  (Measured: ramping device-resident input only adds launches.)
+  // host input on the pipeline: ramp the first chunks up from chunk/8 so that the H2D copy that nothing can hide
+  // (the very first one) is short.  Growth is x9/8 per chunk: the copy of chunk k+1 must not take longer than
+  // the kernels of chunk k, and PCIe delivers proofs only ~1.3x faster than the GPU verifies them (55 GB/s =
+  // 4.3e5 S12 proofs/s against 3.3e5) — doubling left the GPU idle for ~25 ms per call waiting for copies.
+  // Measured at 10^5 S12 proofs from pinned memory (tools/ramp_sweep.sh): x2 292k, x1.5 296k, x1.25 300k,
+  // x1.125 319k, x1.0625 313k proofs/s; constant chunks of 2-8 k proofs 238k-308k.
+  // (Measured: ramping device-resident input only adds launches.)
   size_t ramp = (!src_dev && depth == 2 && chunk >= 8 * 1024) ? chunk / 8 / 32 * 32 : chunk;
   for (size_t c0 = 0, m = 0; c0 < n; c0 += m, k++) {
     m = std::min(ramp, n - c0);
-    ramp = std::min(chunk, ramp * 2);
+    ramp = std::min(chunk, (ramp * P2V_RAMP_NUM / P2V_RAMP_DEN + 31) / 32 * 32);
     const u64 *src = blobs + c0 * blob_words;
     int b = k & 1;
     cudaStream_t st = streams[depth == 2 ? b : 0];

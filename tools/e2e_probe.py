@@ -6,6 +6,8 @@ import fixtures, plonky2_verifier_b200 as p2v
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
 shape, lay, vkey, blob = fixtures.load("s12")
 ctx = p2v.Context(0); cir = p2v.Circuit(ctx, shape, vkey)
+if len(sys.argv) > 2:
+    ctx.set_chunk(int(sys.argv[2]))
 W = lay.blob_words
 h = torch.empty((n, W), dtype=torch.int64, pin_memory=True)
 hb = h.numpy().view(np.uint64); hb[:] = blob
