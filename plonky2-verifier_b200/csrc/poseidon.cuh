@@ -248,11 +248,111 @@ __device__ __forceinline__ void poseidon_mds_mixed(u64 (&s)[12], int next_round)
 #endif
 }
 
+// ---- CRT-split mixed linear layer (POSEIDON_MDS_F64 == 3) ---------------------------------------------------
+// The MDS matrix is circ(c) + 8*E00, and x^12 - 1 = (x^6 - 1)(x^6 + 1): with X+_j = x_j + x_{j+6},
+// X-_j = x_j - x_{j+6} (j < 6),  p_d = c_d + c_{d+6} = (30,28,80,34,36,48),  q_d = c_d - c_{d+6} = (4,2,2,-2,-32,8),
+// q_{d+6} = -q_d:
+//     S_i = sum_{j<6} p_{(j-i) mod 6} X+_j        D_i = sum_{j<6} q_{(j-i) mod 12} X-_j        (i < 6)
+//     y_i = (S_i + D_i)/2 + [i == 0] 8 x_0         y_{i+6} = (S_i - D_i)/2
+// 2 x 36 multiply-adds per half instead of 144, plus 12 + 12 additions: 25% fewer instructions in the layer.
+// Same two-pipe split as the mixed form (low 43 bits: exact DFMAs, |values| < 2^53; high 21 bits: 32-bit IMADs,
+// wrap-around signed arithmetic with a true result in [0, 2^31.1)).  The halving is free: it rides on the
+// magic-number add for the low part (fma(T, 0.5, 2^52)) and on the shift amounts of the fold for the high part.
+// Round constants enter as seeds: S_i <- rc_i + rc_{i+6}, D_i <- rc_i - rc_{i+6}.
+#define POSEIDON_MDS_P {30, 28, 80, 34, 36, 48}
+#define POSEIDON_MDS_Q {4, 2, 2, -2, -32, 8}
+struct PoseidonRcCrt {
+  double s_lo[31][6], d_lo[31][6];
+  u32 s_hi[31][6], d_hi[31][6];  // d_hi: two's complement
+};
+constexpr PoseidonRcCrt poseidon_make_rc_crt() {
+  constexpr u64 rc[360] = P2V_ALL_ROUND_CONSTANTS;
+  PoseidonRcCrt t{};
+  for (int r = 0; r < 30; r++)
+    for (int i = 0; i < 6; i++) {
+      u64 a = rc[r * 12 + i], b = rc[r * 12 + i + 6];
+      double al = (double)(a & ((1ULL << 43) - 1)), bl = (double)(b & ((1ULL << 43) - 1));
+      t.s_lo[r][i] = al + bl;
+      t.d_lo[r][i] = al - bl;
+      t.s_hi[r][i] = (u32)(a >> 43) + (u32)(b >> 43);
+      t.d_hi[r][i] = (u32)(a >> 43) - (u32)(b >> 43);
+    }
+  return t;
+}
+static __constant__ PoseidonRcCrt c_rcc = poseidon_make_rc_crt();
+
+// input pairs 1..5 first, pair 0 (the one lane 0 feeds) LAST — see poseidon_mds_acc_mixed
+template <int I, int J>
+__device__ __forceinline__ void poseidon_crt_acc(double &S, double &D, u32 &Sh, u32 &Dh, const double (&xp)[6], const double (&xm)[6],
+                                                 const u32 (&hp)[6], const u32 (&hm)[6]) {
+  constexpr int Pc[6] = POSEIDON_MDS_P;
+  constexpr int Qc[6] = POSEIDON_MDS_Q;
+  constexpr int d = (J - I + 12) % 12;
+  constexpr int pc = Pc[d % 6];
+  constexpr int qc = d < 6 ? Qc[d] : -Qc[d - 6];
+  S = fma(xp[J], (double)pc, S);
+  D = fma(xm[J], (double)qc, D);
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(Sh) : "r"(hp[J]), "n"(pc));
+  asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(Dh) : "r"(hm[J]), "n"(qc));
+  if constexpr (J == 0) return;
+  else if constexpr (J + 1 < 6) poseidon_crt_acc<I, J + 1>(S, D, Sh, Dh, xp, xm, hp, hm);
+  else poseidon_crt_acc<I, 0>(S, D, Sh, Dh, xp, xm, hp, hm);
+}
+// value = T/2 + 2^43 * (Th/2):  T < 2^53 even (exact double), Th < 2^31.1 even
+__device__ __forceinline__ u64 poseidon_crt_fold(double T, u32 Th) {
+  double L = fma(T, 0.5, P2V_TWO52);
+  u32 Ll = (u32)__double2loint(L), Lh = (u32)__double2hiint(L) & 0xFFFFFu;
+  u32 r0, r1;
+  asm("{\n\t.reg .u32 t,w2,c;\n\t"
+      "shl.b32 t,%4,10;\n\tadd.cc.u32 %1,%3,t;\n\t"          // w1 = Lh + ((Th/2) << 11)
+      "shr.u32 w2,%4,22;\n\taddc.u32 w2,w2,0;\n\t"           // w2 = ((Th/2) >> 21) + carry
+      "add.cc.u32 %1,%1,w2;\n\taddc.u32 c,0,0;\n\t"
+      "add.u32 w2,w2,c;\n\tadd.u32 %1,%1,c;\n\t"
+      "sub.cc.u32 %0,%2,w2;\n\tsubc.u32 %1,%1,0;\n\t}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"(Ll), "r"(Lh), "r"(Th));
+  return ((u64)r1 << 32) | r0;
+}
+template <int I>
+__device__ __forceinline__ void poseidon_crt_row(u64 (&s)[12], const double (&xp)[6], const double (&xm)[6], const u32 (&hp)[6],
+                                                 const u32 (&hm)[6], double lo0, u32 hi0, int next_round) {
+  double S = c_rcc.s_lo[next_round][I], D = c_rcc.d_lo[next_round][I];
+  u32 Sh = c_rcc.s_hi[next_round][I], Dh = c_rcc.d_hi[next_round][I];
+  poseidon_crt_acc<I, 1>(S, D, Sh, Dh, xp, xm, hp, hm);
+  double T = S + D, U = S - D;
+  u32 Th = Sh + Dh, Uh = Sh - Dh;
+  if constexpr (I == 0) {  // + 8 x_0 on the diagonal (doubled like everything else before the halving)
+    T = fma(lo0, 16.0, T);
+    asm("mad.lo.u32 %0, %1, 16, %0;" : "+r"(Th) : "r"(hi0));
+  }
+  s[I] = poseidon_crt_fold(T, Th);
+  s[I + 6] = poseidon_crt_fold(U, Uh);
+  if constexpr (I + 1 < 6) poseidon_crt_row<I + 1>(s, xp, xm, hp, hm, lo0, hi0, next_round);
+}
+__device__ __forceinline__ void poseidon_mds_crt(u64 (&s)[12], int next_round) {
+  double lo[12], xp[6], xm[6];
+  u32 hi[12], hp[6], hm[6];
+#pragma unroll
+  for (int j = 0; j < 12; j++) {
+    u32 xl = (u32)s[j], xh = (u32)(s[j] >> 32);
+    lo[j] = __hiloint2double((int)(0x43300000u | (xh & 0x7FFu)), (int)xl) - P2V_TWO52;
+    hi[j] = xh >> 11;
+  }
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    xp[j] = lo[j] + lo[j + 6];
+    xm[j] = lo[j] - lo[j + 6];
+    hp[j] = hi[j] + hi[j + 6];
+    hm[j] = hi[j] - hi[j + 6];
+  }
+  poseidon_crt_row<0>(s, xp, xm, hp, hm, lo[0], hi[0], next_round);
+}
+
 #ifndef POSEIDON_MDS_SEPARATE_OUT
 #define POSEIDON_MDS_SEPARATE_OUT 0
 #endif
 #ifndef POSEIDON_MDS_F64
-#define POSEIDON_MDS_F64 2
+#define POSEIDON_MDS_F64 3
 #endif
 
 // The permutation.  Input: lazy u64 (any values); output: lazy u64 (apply gl_canon before use as data).
@@ -277,7 +377,9 @@ __device__ __forceinline__ void poseidon_permute(u64 (&s)[12]) {
     } else {
       s[0] = poseidon_sbox(s[0]);
     }
-#if POSEIDON_MDS_F64 == 2
+#if POSEIDON_MDS_F64 == 3
+    poseidon_mds_crt(s, r + 1);
+#elif POSEIDON_MDS_F64 == 2
     poseidon_mds_mixed(s, r + 1);
 #elif POSEIDON_MDS_F64
     poseidon_mds_f64(s, r + 1);
