@@ -45,19 +45,24 @@ __device__ __forceinline__ u64 gl_sub(u64 a, u64 b) {
 }
 __device__ __forceinline__ u64 gl_neg(u64 a) { return gl_sub(0, a); }
 
-// (hi:lo) mod p, 128-bit input, lazy 64-bit output: carry-chain form (13 integer ops, no compares/selects)
-//   t = (w1:w0) - w3, minus EPS on borrow;  u = w2*(2^32-1) = (w2<<32) - w2;  r = t + u, plus EPS on carry.
+// (hi:lo) mod p, 128-bit input, lazy 64-bit output: carry-chain form (no compares/selects)
+//   t = (w1:w0) - w3, minus EPS on borrow;  r = t + w2*(2^32-1), plus EPS on carry.
+// The multiply-add pair mad.lo.cc / madc.hi.cc becomes ONE IMAD.HI.U32 with carry-out (+ an IMAD.IADD for the low
+// word, which is just t0 - w2).  The carry c is applied as r0 = t0 - c, r1 = t1 - borrow + c (3 instructions; the
+// mask form add.cc m / addc 0 compiled to 5).  10 SASS instructions per reduction instead of 15.  ptxas equalises
+// the instruction COUNTS of the FMA and ALU pipes (IMAD.X / IMAD.MOV / IMAD.IADD stand in for IADD3 / MOV) as if
+// IMAD.WIDE and IMAD.HI cost one slot; they cost two, so what the s-box phase minimises is (instructions + 2 x wide
+// multiplies) — measured on a 4-s-box loop: 356+128 (shift form) -> 308+160 -> 276+160.
 // Neither correction can wrap twice: after a borrow t >= 2^64 - 2^32 + 1, and a wrapped r is < u <= 2^64 - 2^33 + 1.
 // NOTE on flags: `subc m,0,0` right after a SUB chain yields the borrow mask, but after an ADD chain ptxas feeds the
 // raw hardware carry into it (inverted meaning), so carries are materialised with addc + neg instead.
 __device__ __forceinline__ u64 gl_reduce128(u64 lo, u64 hi) {
   u32 w0 = (u32)lo, w1 = (u32)(lo >> 32), w2 = (u32)hi, w3 = (u32)(hi >> 32), r0, r1;
-  asm("{\n\t.reg .u32 m,t0,t1,u0,u1;\n\t"
+  asm("{\n\t.reg .u32 m,t0,t1;\n\t"
       "sub.cc.u32 t0,%2,%5;\n\tsubc.cc.u32 t1,%3,0;\n\tsubc.u32 m,0,0;\n\t"
       "sub.cc.u32 t0,t0,m;\n\tsubc.u32 t1,t1,0;\n\t"
-      "sub.cc.u32 u0,0,%4;\n\tsubc.u32 u1,%4,0;\n\t"
-      "add.cc.u32 t0,t0,u0;\n\taddc.cc.u32 t1,t1,u1;\n\taddc.u32 m,0,0;\n\tneg.s32 m,m;\n\t"
-      "add.cc.u32 %0,t0,m;\n\taddc.u32 %1,t1,0;\n\t}"
+      "mad.lo.cc.u32 t0,%4,0xffffffff,t0;\n\tmadc.hi.cc.u32 t1,%4,0xffffffff,t1;\n\taddc.u32 m,0,0;\n\t"
+      "sub.cc.u32 %0,t0,m;\n\tsubc.u32 t1,t1,0;\n\tadd.u32 %1,t1,m;\n\t}"   // + c*EPS = + (c << 32) - c
       : "=r"(r0), "=r"(r1)
       : "r"(w0), "r"(w1), "r"(w2), "r"(w3));
   return ((u64)r1 << 32) | r0;
