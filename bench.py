@@ -176,7 +176,8 @@ def main():
         raise SystemExit("bench.py needs a GPU: libp2v has no CPU fallback")
     torch.cuda.set_device(local_rank)
     from plonky2_verifier_b200 import sharding
-    prev_affinity = sharding.bind_to_gpu_numa_node(local_rank)  # pinned staging buffers on the GPU's NUMA node
+    # pinned staging buffers on the GPU's NUMA node (P2V_NO_NUMA_BIND=1 leaves the affinity alone: tuning aid)
+    prev_affinity = os.sched_getaffinity(0) if os.environ.get("P2V_NO_NUMA_BIND") else sharding.bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -288,10 +289,15 @@ def main():
     barrier()
     e2e_steps = max(2, args.steps)
     t0 = time.perf_counter()
+    step_ms = []
     for _ in range(e2e_steps):
+        t1 = time.perf_counter()
         step_host()
+        step_ms.append((time.perf_counter() - t1) * 1e3)
     ctx.sync()
     dt = time.perf_counter() - t0
+    if os.environ.get("P2V_TRACE"):
+        sys.stderr.write("[bench] e2e steps (ms): %s, total %.1f ms\n" % (", ".join("%.1f" % x for x in step_ms), dt * 1e3))
     te = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

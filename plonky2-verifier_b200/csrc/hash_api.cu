@@ -38,6 +38,16 @@ int p2v_ctx_create(int device, p2v_ctx **out) {
     P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming));
     P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->compute_done[i], cudaEventDisableTiming));
   }
+  {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    P2V_CUDA(nullptr, cudaMemPoolCreate(&ctx->pool, &props));
+    uint64_t keep = UINT64_MAX;
+    P2V_CUDA(nullptr, cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   *out = ctx;
   return P2V_OK;
 }
@@ -50,6 +60,7 @@ void p2v_ctx_destroy(p2v_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream2);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws2) cudaFree(ctx->ws2);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
   cudaStreamDestroy(ctx->stream2);

@@ -1,6 +1,9 @@
 // C-ABI entry points for circuits and proof batches: p2v_circuit_create, p2v_challenges,
 // p2v_constraints, p2v_fri, p2v_verify_batch, p2v_synth_batch.  See include/p2v.h.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include "constraints.cuh"
@@ -239,11 +242,15 @@ __global__ void k_lookup_delta_copies(DevCircuit c, Workspace ws, size_t n) {
     }
 }
 
+// P2V_TRACE=1 in the environment: per-chunk timeline of the pipelined path on stderr (tuning aid; adds events only)
+struct TracePoint { const char *what; int chunk; size_t m; cudaEvent_t ev; };
 #ifndef P2V_RAMP_NUM
 #define P2V_RAMP_NUM 9
 #define P2V_RAMP_DEN 8
 #endif
 int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t n, int what, Outputs out) {
+  auto host_t0 = std::chrono::steady_clock::now();
+  auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
   if (!ctx || !cir || !blobs) return p2v_fail(ctx, P2V_E_INVALID, "NULL argument");
   if (cir->ctx != ctx) return p2v_fail(ctx, P2V_E_INVALID, "circuit belongs to another context");
   if (n == 0) return P2V_OK;
@@ -289,6 +296,17 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->fork_ev, 0));
   }
   const bool timed = depth == 1;
+  static const bool trace_on = getenv("P2V_TRACE") != nullptr;
+  std::vector<TracePoint> trace;
+  auto mark = [&](const char *what, int chunk_i, size_t m_i, cudaStream_t s) {
+    if (!trace_on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    trace.push_back({what, chunk_i, m_i, e});
+  };
+  double host_setup = host_ms();
+  mark("begin", -1, 0, ctx->stream);
   int k = 0;
   // host input on the pipeline: ramp the first chunks up from chunk/8 so that the H2D copy that nothing can hide
   // (the very first one) is short.  Growth is x9/8 per chunk: the copy of chunk k+1 must not take longer than
@@ -309,8 +327,10 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
       // double-buffered staging: the H2D copy of chunk k+1 overlaps the kernels of chunk k; buffer b is free
       // again once the K0 that read it (chunk k-2) has finished
       P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done[b], 0));
+      mark("copy_start", k, m, ctx->copy_stream);
       P2V_CUDA(ctx, cudaMemcpyAsync(ctx->stage_buf[b], src, m * blob_words * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
       P2V_CUDA(ctx, cudaEventRecord(ctx->copy_done[b], ctx->copy_stream));
+      mark("copy_end", k, m, ctx->copy_stream);
       P2V_CUDA(ctx, cudaStreamWaitEvent(st, ctx->copy_done[b], 0));
       src = (const u64 *)ctx->stage_buf[b];
     }
@@ -321,6 +341,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
       P2V_LAUNCH_ON(ctx, st, k_stage_transpose, grid, 256, 0, src, m, (int)blob_words, d.L.proof_words, d.L.query_words, d.Q, ws.pp, ws.qp);
     }
     if (!src_dev) P2V_CUDA(ctx, cudaEventRecord(ctx->compute_done[b], st));
+    mark("k0_end", k, m, st);
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     // K4
     P2V_LAUNCH_ON(ctx, st, k_challenges, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
@@ -329,6 +350,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     // K5
     if (what & RUN_CONSTRAINTS) P2V_LAUNCH_ON(ctx, st, k_constraints, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    mark("k5_end", k, m, st);
     // K6
     if (what & RUN_FRI) {
       size_t items = m * (size_t)d.Q * (4 + d.nsteps);
@@ -347,6 +369,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
       P2V_LAUNCH_ON(ctx, st, k_verdict, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m, out.verdict_mode, stp, bits);
     }
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    mark("chunk_end", k, m, st);
     // optional intermediate outputs
     if (o_ch.dev) P2V_LAUNCH_ON(ctx, st, k_copy_planes, p2v_grid_for(ctx, m * d.ch_words, 256, 8), 256, 0, ws.ch, m, d.ch_words, o_ch.as<u64>(), n, c0);
     if (o_comb.dev) P2V_LAUNCH_ON(ctx, st, k_copy_planes, p2v_grid_for(ctx, m * 2 * d.r, 256, 8), 256, 0, ws.comb, m, 2 * d.r, o_comb.as<u64>(), n, c0);
@@ -359,6 +382,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     P2V_CUDA(ctx, cudaEventRecord(ctx->join_ev, ctx->stream2));
     P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
   }
+  double host_issued = host_ms();
   bool any_host = false;
   for (DevOut *o : {&o_ch, &o_comb, &o_eq, &o_status, &o_bits, &o_qs, &o_folded}) {
     if ((rc = o->finish())) return rc;
@@ -366,6 +390,18 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   }
   if (any_host) {
     P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if (trace_on) {
+    double host_synced = host_ms();
+    P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    fprintf(stderr, "[p2v trace] host: setup %.3f ms, all chunks issued %.3f ms, outputs synced %.3f ms (n = %zu, %s input)\n", host_setup,
+            host_issued, host_synced, n, src_dev ? "device" : "host");
+    for (auto &t : trace) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, trace[0].ev, t.ev);
+      fprintf(stderr, "[p2v trace] %8.3f ms  chunk %3d (%6zu proofs)  %s\n", ms, t.chunk, t.m, t.what);
+    }
+    for (auto &t : trace) cudaEventDestroy(t.ev);
   }
   ctx->last_ms.clear();
   if (timed) ctx->last_ms["_pending"] = 1.0f;
