@@ -135,13 +135,14 @@ size_t carve(const DevCircuit &d, size_t m, char *base, Workspace *ws, bool want
   u64 *ch = (u64 *)take((size_t)d.ch_words * m * 8);
   u64 *pih = (u64 *)take(4 * m * 8);
   u64 *pre = (u64 *)take(4 * m * 8);
+  u64 *apow = (u64 *)take((size_t)2 * d.n_first * m * 8);
   u64 *comb = (u64 *)take((size_t)2 * d.r * m * 8);
   u32 *qstat = (u32 *)take((size_t)d.Q * m * 4);
   uint8_t *tree_ok = (uint8_t *)take((size_t)(4 + d.nsteps) * d.Q * m);
   u64 *folded = want_folded ? (u64 *)take((size_t)2 * d.Q * m * 8) : nullptr;
   uint8_t *eq = (uint8_t *)take(m);
   if (ws) {
-    ws->pp = pp; ws->qp = qp; ws->ch = ch; ws->pih = pih; ws->pre = pre; ws->comb = comb; ws->qstat = qstat;
+    ws->pp = pp; ws->qp = qp; ws->ch = ch; ws->pih = pih; ws->pre = pre; ws->apow = apow; ws->comb = comb; ws->qstat = qstat;
     ws->folded = folded; ws->eqmask = eq; ws->tree_ok = tree_ok;
   }
   return off;
@@ -483,9 +484,10 @@ int p2v_circuit_create(p2v_ctx *ctx, const p2v_shape *shape, const uint64_t *vke
   d.ch_fri_alpha = d.ch_zeta + 2; d.ch_fri_betas = d.ch_fri_alpha + 2; d.ch_pow = d.ch_fri_betas + 2 * d.nsteps;
   d.ch_idx = d.ch_pow + 1; d.ch_words = d.ch_idx + d.Q;
   d.omega = hroot(d.degree_bits);
+  d.n_first = L.oracle_width[0] + L.oracle_width[1] + L.oracle_width[2] + L.oracle_width[3];
   // device tables
   size_t n_lut_words = 2 * (size_t)(shape->num_luts ? shape->lut_off[shape->num_luts] : 0);
-  size_t words = (size_t)L.vkey_words + P2V_MAX_ROUTED + P2V_MAX_WEIGHTS + n_lut_words + 128;
+  size_t words = (size_t)L.vkey_words + P2V_MAX_ROUTED + P2V_MAX_WEIGHTS + n_lut_words + TAB_WORDS;
   std::vector<u64> h(words, 0);
   size_t o_vkey = 0, o_kis = o_vkey + L.vkey_words, o_w = o_kis + P2V_MAX_ROUTED, o_lut = o_w + P2V_MAX_WEIGHTS, o_tab = o_lut + n_lut_words;
   memcpy(&h[o_vkey], vkey, (size_t)L.vkey_words * 8);
@@ -500,6 +502,10 @@ int p2v_circuit_create(p2v_ctx *ctx, const p2v_shape *shape, const uint64_t *vke
     for (int k = 0; k < 32; k++) {
       h[o_tab + TAB_ETA + k] = eta; h[o_tab + TAB_INV_ETA + k] = ieta; h[o_tab + TAB_G + k] = g; h[o_tab + TAB_INV_G + k] = ig;
       eta = hmul(eta, eta); ieta = hmul(ieta, ieta); g = hmul(g, g); ig = hmul(ig, ig);
+    }
+    for (int a = 1; a <= 8; a++) {  // inverse roots of unity of every possible folding arity
+      uint64_t iw = hinv(hroot(a)), x = 1;
+      for (int e = 0; e < (1 << a); e++) { h[o_tab + TAB_INVW + (1 << a) + e] = x; x = hmul(x, iw); }
     }
   }
   P2V_CUDA(ctx, cudaMalloc(&c->d_blob, words * 8));

@@ -34,12 +34,14 @@ struct DevCircuit {
   TOp ops[P2V_MAX_TOPS];
   // offsets of the challenge planes (include/p2v.h "Challenges of one proof")
   int32_t ch_betas, ch_gammas, ch_alphas, ch_deltas, ch_zeta, ch_fri_alpha, ch_fri_betas, ch_pow, ch_idx, ch_words;
+  int32_t n_first;       // length of the first FRI batch = sum of the four oracle widths (powers of alpha kept per proof)
   // device-resident tables
   const u64 *vkey;       // cap [2^cap_height][4] ++ circuit_digest[4]
   const u64 *k_is;       // [num_routed]
   const u64 *weights;    // barycentric weights
   const u64 *lut_pairs;  // (inp,out) pairs
-  const u64 *tab;        // [4][32]: eta^(2^k), eta^-(2^k), g^(2^k), g^-(2^k)   (eta = LDE generator, g = mulGen)
+  const u64 *tab;        // [4][32]: eta^(2^k), eta^-(2^k), g^(2^k), g^-(2^k)   (eta = LDE generator, g = mulGen),
+                         // then TAB_INVW: entry 2^a + e = subgroupGenerator(a)^-e for a in 1..8, e < 2^a
   u64 omega;             // subgroupGenerator(degree_bits)
   u64 inv_arity[P2V_MAX_STEPS];  // 1/2^arity_bits
   u64 inv_omega[P2V_MAX_STEPS];  // subgroupGenerator(arity_bits)^-1
@@ -48,6 +50,8 @@ struct DevCircuit {
 #define TAB_INV_ETA 32
 #define TAB_G 64
 #define TAB_INV_G 96
+#define TAB_INVW 128
+#define TAB_WORDS (128 + 512)
 
 // Per-chunk workspace planes
 struct Workspace {
@@ -56,6 +60,7 @@ struct Workspace {
   u64 *ch;     // [ch_words][n]   challenges (canonical)
   u64 *pih;    // [4][n]          sponge(public_inputs)
   u64 *pre;    // [4][n]          precomputed reduced openings Y0, Y1 (Plonk/FRI.hs:128-134)
+  u64 *apow;   // [2*n_first][n]  alpha_fri^k, k < n_first (K4 -> K6b: combineInitial as a plain dot product)
   u64 *comb;   // [2r][n]         combined constraints
   u32 *qstat;  // [Q][n]          per-query status
   uint8_t *tree_ok;  // [4+nsteps][Q][n]  Merkle opening verdicts (K6a -> K6b)
@@ -76,6 +81,17 @@ __device__ __forceinline__ u64 pow_from_table(const u64 *__restrict__ tab, u32 e
   }
   return acc;
 }
+
+// sum of 64x64-bit products kept as an exact 192-bit integer; 2^128 = 2^96 * 2^32 = -2^32 (mod p)
+struct DotAcc {
+  u64 lo = 0, hi = 0;
+  u32 top = 0;
+  __device__ __forceinline__ void mac(u64 a, u64 x) {
+    unsigned __int128 m = (unsigned __int128)a * x;
+    asm("add.cc.u64 %0,%0,%3;\n\taddc.cc.u64 %1,%1,%4;\n\taddc.u32 %2,%2,0;" : "+l"(lo), "+l"(hi), "+r"(top) : "l"((u64)m), "l"((u64)(m >> 64)));
+  }
+  __device__ __forceinline__ u64 reduce() const { return gl_sub(gl_reduce128(lo, hi), (u64)top << 32); }
+};
 
 // ---- K0: AoS blobs -> SoA planes -----------------------------------------------------------------
 // 32x32 tiles through shared memory: reads are coalesced along the blob (256 B per proof row),
@@ -233,6 +249,15 @@ __global__ void __launch_bounds__(128) k_challenges(const __grid_constant__ DevC
         y1 = gl2_add(x, gl2_mul(alpha, y1));
       }
     }
+    {  // alpha^k for K6b: G = sum alpha^k col_k costs 2 multiplications per column there instead of Horner's 5
+      gl2 ap = gl2_make(1, 0);
+#pragma unroll 1
+      for (int k = 0; k < c.n_first; k++) {
+        ws.apow[(size_t)(2 * k) * n + p] = ap.a;
+        ws.apow[(size_t)(2 * k + 1) * n + p] = ap.b;
+        ap = gl2_mul(ap, alpha);
+      }
+    }
     ws.pre[0 * n + p] = gl_canon(y0.a);
     ws.pre[1 * n + p] = gl_canon(y0.b);
     ws.pre[2 * n + p] = gl_canon(y1.a);
@@ -350,47 +375,65 @@ __global__ void __launch_bounds__(256) k_fri_query(const __grid_constant__ DevCi
     int npp = (c.num_routed + c.qdf - 1) / c.qdf;  // divCeil routed qdf
     int w2 = L.oracle_width[2];
     int n_pp = r * npp < w2 ? r * npp : w2;        // splitAt (r*npp)
-    // firstBatch = constants ++ witness ++ oracle_pp ++ quotient ++ oracle_lookup, Horner from the end
-    gl2 g0 = gl2_make(0, 0);
+    // firstBatch = constants ++ witness ++ oracle_pp ++ quotient ++ oracle_lookup:  G0 = sum_k alpha^k col_k with the
+    // per-proof powers of K4; the 128-bit products are accumulated unreduced (192 bits) and reduced once.
+    const u64 *__restrict__ apw = ws.apow + p;
+    gl2 g0, g1;
+    int n_second = 0;
     {
       int seg_off[5] = {L.q_off_leaf[0], L.q_off_leaf[1], L.q_off_leaf[2], L.q_off_leaf[3], L.q_off_leaf[2] + n_pp};
       int seg_n[5] = {L.oracle_width[0], L.oracle_width[1], n_pp, L.oracle_width[3], w2 - n_pp};
+      DotAcc re, im;
+      int k = 0;
 #pragma unroll 1
-      for (int sg = 4; sg >= 0; sg--) {
-#pragma unroll 1
-        for (int i = seg_n[sg] - 1; i >= 0; i--) {
+      for (int sg = 0; sg < 5; sg++) {
+#pragma unroll 2
+        for (int i = 0; i < seg_n[sg]; i++, k++) {
           u64 x = qbase[(size_t)(seg_off[sg] + i) * qstride];
-          g0 = gl2_add_base(gl2_mul(alpha, g0), x);
+          re.mac(apw[(size_t)(2 * k) * n], x);
+          im.mac(apw[(size_t)(2 * k + 1) * n], x);
         }
       }
+      g0 = gl2_make(re.reduce(), im.reduce());
     }
     // secondBatch = take r oracle_pp ++ oracle_lookup
-    gl2 g1 = gl2_make(0, 0);
-    int n_second = 0;
     {
       int take_r = r < n_pp ? r : n_pp;
       int seg_off[2] = {L.q_off_leaf[2], L.q_off_leaf[2] + n_pp};
       int seg_n[2] = {take_r, w2 - n_pp};
       n_second = seg_n[0] + seg_n[1];
+      DotAcc re, im;
+      int k = 0;
 #pragma unroll 1
-      for (int sg = 1; sg >= 0; sg--) {
+      for (int sg = 0; sg < 2; sg++) {
 #pragma unroll 1
-        for (int i = seg_n[sg] - 1; i >= 0; i--) {
+        for (int i = 0; i < seg_n[sg]; i++, k++) {
           u64 x = qbase[(size_t)(seg_off[sg] + i) * qstride];
-          g1 = gl2_add_base(gl2_mul(alpha, g1), x);
+          re.mac(apw[(size_t)(2 * k) * n], x);
+          im.mac(apw[(size_t)(2 * k + 1) * n], x);
         }
       }
+      g1 = gl2_make(re.reduce(), im.reduce());
     }
     gl2 y0 = gl2_make(ws.pre[0 * n + p], ws.pre[1 * n + p]);
     gl2 y1 = gl2_make(ws.pre[2 * n + p], ws.pre[3 * n + p]);
     // point_x = mulGen * eta^rev(idx)
     u64 point_x = gl_mul(GL_MUL_GEN_C, pow_from_table(c.tab + TAB_ETA, bitrev(idx, c.lde_bits)));
     gl2 loc1 = gl2_scale(c.omega, zeta);
-    gl2 one = gl2_mul(gl2_sub(g0, y0), gl2_inv(gl2_make(gl_sub(point_x, zeta.a), gl_neg(zeta.b))));
-    gl2 two = gl2_mul(gl2_sub(g1, y1), gl2_inv(gl2_make(gl_sub(point_x, loc1.a), gl_neg(loc1.b))));
-    gl2 apow = gl2_make(1, 0);
-#pragma unroll 1
-    for (int i = 0; i < n_second; i++) apow = gl2_mul(apow, alpha);
+    // the two divisions share one inversion (inv 0 = 0 is kept: a zero denominator takes the separate path)
+    gl2 den0 = gl2_make(gl_sub(point_x, zeta.a), gl_neg(zeta.b)), den1 = gl2_make(gl_sub(point_x, loc1.a), gl_neg(loc1.b));
+    gl2 inv0, inv1;
+    if (gl2_eq(den0, gl2_make(0, 0)) || gl2_eq(den1, gl2_make(0, 0))) {
+      inv0 = gl2_inv(den0);
+      inv1 = gl2_inv(den1);
+    } else {
+      gl2 ip = gl2_inv(gl2_mul(den0, den1));
+      inv0 = gl2_mul(ip, den1);
+      inv1 = gl2_mul(ip, den0);
+    }
+    gl2 one = gl2_mul(gl2_sub(g0, y0), inv0);
+    gl2 two = gl2_mul(gl2_sub(g1, y1), inv1);
+    gl2 apow = gl2_make(apw[(size_t)(2 * n_second) * n], apw[(size_t)(2 * n_second + 1) * n]);  // n_second <= w2 < n_first
     gl2 eval = gl2_add(gl2_mul(apow, one), two);
 
     // ---------------- folding steps (Plonk/FRI.hs:306-323) ----------------
@@ -409,24 +452,36 @@ __global__ void __launch_bounds__(256) k_fri_query(const __grid_constant__ DevCi
       // inverse tables: shift = g^(2^cum), eta_big = eta^(2^cum)   (prepareCoset :248-259)
       u32 start = bitrev((qidx >> a) << a, bits);
       u64 inv_ofs = gl_mul(__ldg(c.tab + TAB_INV_G + c.cum_bits[st]), pow_from_table(c.tab + TAB_INV_ETA + c.cum_bits[st], start));
-      // foldCosetWith (:263-279): (1/A) sum_k beta^k sum_j (ofs w^j)^-k v_j  =  (1/A) sum_j v_j S(t_j),
-      // t_j = beta/(ofs w^j),  S(t) = sum_{k<A} t^k = prod_{i<a} (1 + t^(2^i));  v = bit-reversed evals
+      // foldCosetWith (:263-279) is the value at beta of the interpolant P through (ofs w^j, v_j), j < A.  Computed
+      // as `a` radix-2 folds (the FRI recursion itself): P(x) = Pe(x^2) + x Po(x^2) gives on each pair of opposite
+      // points  g(x_j^2) = [ (v_j + v_{j+A/2}) + (beta / x_j)(v_j - v_{j+A/2}) ] / 2  and  P(beta) = g(beta^2);
+      // level l uses beta^(2^l), ofs^(2^l), w^(2^l).  The evals are stored bit-reversed, so every level pairs
+      // ADJACENT entries and its output is again bit-reversed: one streaming pass with a stack of `a` partial
+      // results.  15 combines of 7 multiplications for A = 16 (the closed form with S(t) = prod (1 + t^(2^i)) took
+      // 47 per point); the 1/2 of every level is applied once as 1/A.  Same field element, bit for bit.
       gl2 beta = gl2_make(ws.ch[(size_t)(c.ch_fri_betas + 2 * st) * n + p], ws.ch[(size_t)(c.ch_fri_betas + 2 * st + 1) * n + p]);
-      gl2 tj = gl2_scale(inv_ofs, beta);
-      u64 inv_w = c.inv_omega[st];
+      gl2 tl[8], stack[8];
+      tl[0] = gl2_scale(inv_ofs, beta);
+#pragma unroll 1
+      for (int l = 1; l < a; l++) tl[l] = gl2_sqr(tl[l - 1]);
+      const u64 *__restrict__ winv = c.tab + TAB_INVW + A;
       gl2 acc = gl2_make(0, 0);
 #pragma unroll 1
-      for (int j = 0; j < A; j++) {
-        u32 src = bitrev((u32)j, a);
-        gl2 v = gl2_make(ev[(size_t)(2 * src) * qstride], ev[(size_t)(2 * src + 1) * qstride]);
-        gl2 S = gl2_make(1, 0), tp = tj;
-#pragma unroll 1
-        for (int i = 0; i < a; i++) {
-          S = gl2_mul(S, gl2_add_base(tp, 1));
-          tp = gl2_sqr(tp);
+      for (int i = 0; i < A; i++) {
+        gl2 cur = gl2_make(ev[(size_t)(2 * i) * qstride], ev[(size_t)(2 * i + 1) * qstride]);
+        u32 ix = (u32)i;
+        int lvl = 0;
+        while (ix & 1u) {
+          u32 pair = ix >> 1;  // pair number at this level in storage order; its natural index is the bit reversal
+          u32 e = bitrev(pair, a - lvl - 1) << lvl;
+          gl2 first = stack[lvl];
+          gl2 f = e ? gl2_scale(__ldg(winv + e), tl[lvl]) : tl[lvl];
+          cur = gl2_add(gl2_add(first, cur), gl2_mul(f, gl2_sub(first, cur)));
+          ix >>= 1;
+          lvl++;
         }
-        acc = gl2_add(acc, gl2_mul(v, S));
-        tj = gl2_scale(inv_w, tj);
+        if (lvl < a) stack[lvl] = cur;
+        acc = cur;
       }
       eval = gl2_scale(c.inv_arity[st], acc);
       qidx >>= a;
