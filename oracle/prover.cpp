@@ -25,7 +25,7 @@
 //
 //   p2v_prover <preset> <out_prefix> [--seed K] [--corrupt-layer S] [--bad-final] [--bad-witness ROW] [--bad-copy]
 //
-// Presets: s12 (standard recursion shape), mid5, small6, fixed4, lookup6 (all-Noop rows, quotient == 0);
+// Presets: s12 (standard recursion shape), mid5, small6, fixed4, arity5, lookup6 (all-Noop rows, quotient == 0);
 //          real5, real7 (ACTIVE gates of all 14 standard kinds on honest witnesses, real quotient C/Z_H).
 #include <chrono>
 #include <cstdio>
@@ -241,6 +241,14 @@ static Preset makePreset(const std::string &name) {
     p.num_wires = 20; p.num_routed = 16; p.num_public_inputs = 3;
     p.gates = {gNoop(), gConst(2), gArith(4), gPI(), gMulExt(3), gArithExt(2)};
     assignGroups(p, {3, 3});
+  } else if (name == "arity5") {
+    // one folding step of arity 32 followed by one of arity 2 (Fixed [5,1]): exercises wide cosets (a > 4)
+    p.degree_bits = 7; p.rate_bits = 1; p.cap_height = 1; p.pow_bits = 5; p.num_queries = 4;
+    p.fixed_strategy = true; p.fixed_arities = {5, 1};
+    p.num_challenges = 2; p.qdf = 2;
+    p.num_wires = 10; p.num_routed = 4; p.num_public_inputs = 1;
+    p.gates = {gNoop(), gConst(2), gPI()};
+    assignGroups(p, {3});
   } else if (name == "fixed4") {
     p.degree_bits = 4; p.rate_bits = 2; p.cap_height = 0; p.pow_bits = 4; p.num_queries = 4;
     p.fixed_strategy = true; p.fixed_arities = {2, 1};

@@ -12,6 +12,7 @@ $P mid5    $G/mid5    --seed 2
 $P small6  $G/small6  --seed 3
 $P fixed4  $G/fixed4  --seed 4
 $P lookup6 $G/lookup6 --seed 5
+$P arity5  $G/arity5  --seed 7   # Fixed [5,1]: a 32-point coset per query
 # real circuit: ACTIVE gates of all 14 standard kinds on honest witnesses, copy constraints (non-identity sigma,
 # real grand product Z + partial products), real quotient polynomial
 $P real5   $G/real5   --seed 6

@@ -53,7 +53,7 @@ def test_python_twin_kat():
     assert pyref.sponge(list(range(1, 10)))[0] == 0x5a90f7c562413c2b
 
 
-@pytest.mark.parametrize("name", ["small6", "fixed4", "lookup6", "mid5", "small6_badfinal", "small6_badlayer0", "small6_badlayer1",
+@pytest.mark.parametrize("name", ["small6", "fixed4", "arity5", "lookup6", "mid5", "small6_badfinal", "small6_badlayer0", "small6_badlayer1",
                                   "real5", "real5_badwitness", "real5_badcopy"])
 def test_twins_agree_on_fixtures(orc, name):
     shape, lay, vkey, blob = fixtures.load(name)
