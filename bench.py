@@ -141,7 +141,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "full verifier on standard-recursion-shape (S12) proofs", "proofs_per_step": per_step,
+        "config": {"workload": "full verifier (challenges + constraints + FRI) on standard-recursion-shape (S12) proofs", "proofs_per_step": per_step,
                    "note": "CPU arm: C++ restatement of the Haskell reference on all host threads (GHC is not in the image)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": "%d proofs per step" % per_step},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
