@@ -107,3 +107,47 @@ def test_chunked_and_device_resident(p2v, ctx, orc):
     cir.synth_batch(blob, n, words, deltas, d_out)
     ctx.sync()
     assert np.array_equal(d_out.cpu().numpy().view(np.uint64), blobs)
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 33])
+def test_ragged_batch_sizes(p2v, ctx, orc, n):
+    """Empty, single and non-multiple-of-32 batches: the packed accept bitmap has ceil(n/32) words, unused bits 0."""
+    cir, shape, lay, vkey, blob = _circuit(p2v, ctx, "real5")
+    blobs, words, deltas = fixtures.tampered_batch(blob, lay, shape, max(n, 1), seed=9, accept_every=3)
+    blobs = blobs[:n]
+    bits = np.full((n + 31) // 32 + 1, 0xDEADBEEF, dtype=np.uint32)  # one guard word behind the bitmap
+    status = np.empty(n, dtype=np.uint32)
+    cir.verifyProof(blobs if n else np.zeros((1, lay.blob_words), dtype=np.uint64), n=n, accept_bits=bits, status=status)
+    assert bits[-1] == 0xDEADBEEF
+    if n == 0:
+        return
+    want = orc.verify_batch(shape, vkey, blobs, threads=2, fast=True)
+    assert np.array_equal(status, want["status"])
+    acc = p2v.unpack_bits(bits[:-1], n)
+    assert np.array_equal(acc, want["status"] == 0)
+    tail = int(bits[(n - 1) // 32]) >> (n % 32) if n % 32 else 0
+    assert tail == 0
+
+
+def test_host_ramped_pipeline_equals_device_resident(p2v, ctx, orc):
+    """Host input with chunks >= 8192 takes the ramped two-stream pipeline (chunk/8 growing x9/8): every proof must
+    land in exactly one chunk.  Compared with the device-resident run of the same batch and, on a sample, the oracle."""
+    import torch
+
+    cir, shape, lay, vkey, blob = _circuit(p2v, ctx, "small6")
+    n = 40000 + 17
+    blobs, words, deltas = fixtures.tampered_batch(blob, lay, shape, n, seed=21, accept_every=5)
+    ctx.set_chunk(8192)
+    try:
+        acc_h, st_h = cir.verifyProof(blobs)
+        d_blobs = torch.from_numpy(blobs.view(np.int64)).cuda()
+        torch.cuda.synchronize()
+        acc_d, st_d = cir.verifyProof(d_blobs, n=n)
+        st_d = np.asarray(st_d.cpu().numpy() if hasattr(st_d, "cpu") else st_d).view(np.uint32)
+    finally:
+        ctx.set_chunk(0)
+    assert np.array_equal(st_h, st_d)
+    sample = np.r_[0:64, 8192 - 32:8192 + 32, n - 64:n]
+    want = orc.verify_batch(shape, vkey, blobs[sample], threads=4, fast=True)
+    assert np.array_equal(st_h[sample], want["status"])
+    assert acc_h[words < 0].all()
