@@ -23,10 +23,11 @@
 // The transcript uses oracle/challenger.hpp (shared with the verifier restatement; the Python
 // twin oracle/pyref.py re-derives the challenges independently).
 //
-//   p2v_prover <preset> <out_prefix> [--seed K] [--corrupt-layer S] [--bad-final] [--bad-witness ROW] [--bad-copy]
+//   p2v_prover <preset> <out_prefix> [--seed K] [--corrupt-layer S] [--bad-final] [--bad-witness ROW] [--bad-copy] [--bad-lookup]
 //
 // Presets: s12 (standard recursion shape), mid5, small6, fixed4, arity5, lookup6 (all-Noop rows, quotient == 0);
-//          real5, real7 (ACTIVE gates of all 14 standard kinds on honest witnesses, real quotient C/Z_H).
+//          real5, real7 (ACTIVE gates of all 14 standard kinds on honest witnesses, real quotient C/Z_H),
+//          reallu6 (real circuit with an honest lookup argument).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -241,6 +242,19 @@ static Preset makePreset(const std::string &name) {
     p.num_wires = 20; p.num_routed = 16; p.num_public_inputs = 3;
     p.gates = {gNoop(), gConst(2), gArith(4), gPI(), gMulExt(3), gArithExt(2)};
     assignGroups(p, {3, 3});
+  } else if (name == "reallu6") {
+    // real circuit WITH a lookup argument: LookupGate rows look entries of a 19-entry table up, LookupTableGate rows hold
+    // the table with the multiplicities, honest RE / partial-sum polynomials per challenge (Plonk/Lookups.hs:45-132)
+    p.real = true;
+    p.degree_bits = 6; p.rate_bits = 3; p.cap_height = 2; p.pow_bits = 8; p.num_queries = 5;
+    p.arity_bits = 3; p.final_poly_bits = 2;
+    p.num_wires = 40; p.num_routed = 24; p.num_public_inputs = 2;
+    p.gates = {gNoop(), gConst(2), gLookup(12), gLookupTable(8, 3), gArith(6), gPI()};
+    assignGroups(p, {4, 2});
+    p.num_lookup_polys = 3;
+    std::vector<std::pair<u64, u64>> t0;
+    for (u64 i = 0; i < 19; i++) t0.push_back({i, (i * i + 3) & 0xffff});
+    p.luts = {t0};
   } else if (name == "arity5") {
     // one folding step of arity 32 followed by one of arity 2 (Fixed [5,1]): exercises wide cosets (a > 4)
     p.degree_bits = 7; p.rate_bits = 1; p.cap_height = 1; p.pow_bits = 5; p.num_queries = 4;
@@ -470,7 +484,7 @@ static std::vector<F> intt(std::vector<F> v, int logn) {
 // ---- the prover ---------------------------------------------------------------------------------------
 struct ProverOut { VerifierOnlyCircuitData vk; ProofWithPublicInputs pw; };
 
-static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, int corrupt_layer, bool bad_final, int threads, int bad_witness_row = -1, bool bad_copy = false) {
+static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, int corrupt_layer, bool bad_final, int threads, int bad_witness_row = -1, bool bad_copy = false, bool bad_lookup = false) {
   SplitMix rng(seed);
   int n = c.degree_bits, N = 1 << n, loglde = c.lde_bits(), M = 1 << loglde;
   int r = c.num_challenges;
@@ -482,6 +496,8 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
   // --- column polynomials (coefficient form, degree < N) ---
   std::vector<std::vector<F>> const_cols, wire_cols, pp_cols, quot_cols;
   std::vector<std::vector<F>> sigma_vals, real_wvals;  // real circuits: sigma and wire columns as values over H
+  std::vector<int> gate_of_row;
+  struct { int slots_lu = 0, slots_lut = 0, lu_start = 0, n_lu_rows = 0, lut_first = 0, n_lut_rows = 0, end_row = 0; } lkp;
   ProverOut out;
   Digest pih;
   if (p.real) {
@@ -489,16 +505,65 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
     SplitMix rpi(seed ^ 0x5EEDF00DULL);
     for (int i = 0; i < c.num_public_inputs; i++) out.pw.public_inputs.push_back(rpi.felt());
     pih = sponge(out.pw.public_inputs);
-    int G = (int)c.gates.size(), ngrp = (int)c.selector_groups.size();
-    std::vector<std::vector<F>> cvals(ngrp + 2, std::vector<F>(N)), wvals(c.num_wires, std::vector<F>(N));
+    int G = (int)c.gates.size(), ngrp = (int)c.selector_groups.size(), nls = c.num_lookup_selectors;
+    std::vector<std::vector<F>> cvals(ngrp + nls + 2, std::vector<F>(N, F(0))), wvals(c.num_wires, std::vector<F>(N));
+    // lookup argument (Plonk/Lookups.hs:45-132): LookupGate rows, then the LookupTableGate rows holding LUT 0 in
+    // REVERSE block order (running evaluation and partial sums accumulate from the end row upwards), then the end row
+    bool has_lut = !c.luts.empty();
+    int lu_gate = -1, lut_gate = -1;
+    for (int k = 0; k < G; k++) {
+      if (c.gates[k].kind == P2V_GATE_LOOKUP) lu_gate = k;
+      if (c.gates[k].kind == P2V_GATE_LOOKUP_TABLE) lut_gate = k;
+    }
+    if (has_lut) {
+      if (lu_gate < 0 || lut_gate < 0) { fprintf(stderr, "real lookup preset needs LookupGate and LookupTableGate\n"); exit(2); }
+      lkp.slots_lu = c.num_routed_wires / 2;
+      lkp.slots_lut = c.num_routed_wires / 3;
+      lkp.lu_start = 10; lkp.n_lu_rows = 2;
+      lkp.lut_first = lkp.lu_start + lkp.n_lu_rows;
+      lkp.n_lut_rows = divCeil((int)c.luts[0].size(), lkp.slots_lut);
+      lkp.end_row = lkp.lut_first + lkp.n_lut_rows;
+      if (lkp.end_row >= N) { fprintf(stderr, "lookup rows do not fit\n"); exit(2); }
+    }
+    std::vector<u64> mult(has_lut ? c.luts[0].size() : 0, 0);
+    gate_of_row.assign(N, 0);
     for (int row = 0; row < N; row++) {
       int gi = row % G;
+      enum { PLAIN, LU, LUT } role = PLAIN;
+      if (has_lut) {
+        if (row >= lkp.lu_start && row < lkp.lut_first) { gi = lu_gate; role = LU; }
+        else if (row >= lkp.lut_first && row < lkp.end_row) { gi = lut_gate; role = LUT; }
+        else if (row == lkp.end_row || gi == lu_gate || gi == lut_gate) gi = noop_index;
+      }
+      gate_of_row[row] = gi;
       for (int g = 0; g < ngrp; g++) cvals[g][row] = g == c.selector_indices[gi] ? F::fromInt(gi) : F((u64)0xFFFFFFFFULL);
+      if (has_lut) {
+        if (role == LUT) cvals[ngrp + LS_TransSre][row] = F(1);
+        if (role == LU) cvals[ngrp + LS_TransLdc][row] = F(1);
+        if (row == lkp.end_row) cvals[ngrp + LS_InitSre][row] = F(1);
+        if (row == lkp.lu_start) cvals[ngrp + LS_LastLdc][row] = F(1);
+        if (row == lkp.lut_first) cvals[ngrp + LS_StartEnd + 0][row] = F(1);
+      }
       F c0 = rng.felt(), c1 = rng.felt();
-      cvals[ngrp][row] = c0; cvals[ngrp + 1][row] = c1;
+      cvals[ngrp + nls][row] = c0; cvals[ngrp + nls + 1][row] = c1;
       std::vector<F> w(c.num_wires);
       for (auto &x : w) x = rng.felt();
-      if (row != bad_witness_row) witnessRow(c.gates[gi], w, c0, c1, pih, rng);  // --bad-witness: leave that row's gate unsatisfied
+      if (role == LU) {            // every slot looks up a random entry of LUT 0
+        for (int i = 0; i < lkp.slots_lu; i++) {
+          size_t t = (size_t)(rng.next() % (u64)c.luts[0].size());
+          if (bad_lookup && row == lkp.lu_start && i == 0) { w[0] = c.luts[0][t].first; w[1] = c.luts[0][t].second + F(1); continue; }  // not in the table
+          w[2 * i] = c.luts[0][t].first; w[2 * i + 1] = c.luts[0][t].second;
+          mult[t]++;
+        }
+      } else if (role == LUT) {    // block q of the table sits in row lut_first + (n_lut_rows - 1 - q); padding = entry 0, multiplicity 0
+        int q = lkp.n_lut_rows - 1 - (row - lkp.lut_first);
+        for (int i = 0; i < lkp.slots_lut; i++) {
+          size_t t = (size_t)q * lkp.slots_lut + i;
+          bool pad = t >= c.luts[0].size();
+          const auto &e = c.luts[0][pad ? 0 : t];
+          w[3 * i] = e.first; w[3 * i + 1] = e.second; w[3 * i + 2] = pad ? F(0) : F(mult[t]);
+        }
+      } else if (row != bad_witness_row) witnessRow(c.gates[gi], w, c0, c1, pih, rng);  // --bad-witness: leave that row's gate unsatisfied
       for (int i = 0; i < c.num_wires; i++) wvals[i][row] = w[i];
     }
     // copy constraints: the routed wires of the Noop rows (unconstrained by any gate) are wired to routed cells of
@@ -512,13 +577,13 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
     {
       std::vector<char> used((size_t)N * R, 0);
       std::vector<int> noop_rows;
-      for (int row = 0; row < N; row++) if (row % G == noop_index) noop_rows.push_back(row);
+      for (int row = 0; row < N; row++) if (gate_of_row[row] == noop_index) noop_rows.push_back(row);
       for (size_t k = 0; k < noop_rows.size(); k++)
         for (int col = 0; col < R; col++) {
           int a = cell(noop_rows[k], col), b;
           if (k > 0 && (col & 1)) b = cell(noop_rows[k - 1], (col * 7 + 3) % R);  // extend an existing cycle
           else
-            do { b = cell((int)(rng.next() % (u64)N), (int)(rng.next() % (u64)R)); } while (used[b] || (b / R) % G == noop_index);
+            do { b = cell((int)(rng.next() % (u64)N), (int)(rng.next() % (u64)R)); } while (used[b] || gate_of_row[b / R] == noop_index);
           used[b] = 1;
           wvals[col][noop_rows[k]] = wvals[b % R][b / R];
           joinCycle(a, b);
@@ -605,7 +670,12 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
   ProofChallenges pch;
   pch.plonk_betas = dx.squeezeN(r);
   pch.plonk_gammas = dx.squeezeN(r);
-  if (c.num_lookup_polys > 0) dx.squeezeN(2 * r);
+  if (c.num_lookup_polys > 0) {
+    std::vector<F> all = pch.plonk_betas, deltas = dx.squeezeN(2 * r);
+    all.insert(all.end(), pch.plonk_gammas.begin(), pch.plonk_gammas.end());
+    all.insert(all.end(), deltas.begin(), deltas.end());
+    pch.plonk_deltas = mkLookupDeltaList(all);
+  }
   if (p.real) {
     // grand product Z and its partial products per challenge round (Plonk/Vanishing.hs:96-111):
     // current = [Z, pp_0 .. pp_{m-1}, Z(omega x)],  current[t+1] = current[t] * numer_t / denom_t  with the routed
@@ -635,6 +705,38 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
     pp_cols.clear();
     for (auto &col : zvals) pp_cols.push_back(intt(col, n));
     for (auto &col : ppvals) pp_cols.push_back(intt(col, n));
+    if (!c.luts.empty()) {
+      // lookup polynomials per challenge round: RE (running evaluation of the table) and the partial sums SLDC_t of the
+      // log-derivative argument, both accumulating from the end row (where they are 0) towards lower row indices:
+      //   table row:  RE(row) = Horner_delta(RE(row+1); inp + B out over the slots),  SLDC_t = prev + sum m/(alpha - (inp + A out))
+      //   lookup row: SLDC_t = prev - sum 1/(alpha - (inp + A out)),   prev of chunk 0 = last SLDC of row+1.
+      int nsl = c.num_lookup_polys - 1, lu_deg = c.quotient_degree_factor - 1, lut_deg = divCeil(lkp.slots_lut, nsl);
+      for (int j = 0; j < r; j++) {
+        const LookupDelta &ld = pch.plonk_deltas[j];
+        std::vector<std::vector<F>> cols(c.num_lookup_polys, std::vector<F>(N, F(0)));
+        F re(0), prev(0);
+        for (int row = lkp.end_row - 1; row >= lkp.lu_start; row--) {
+          bool table = row >= lkp.lut_first;
+          int slots = table ? lkp.slots_lut : lkp.slots_lu, deg = table ? lut_deg : lu_deg, stride = table ? 3 : 2;
+          if (table) {
+            for (int i = 0; i < slots; i++) re = ld.lookup_delta * re + (real_wvals[3 * i][row] + ld.lookup_B * real_wvals[3 * i + 1][row]);
+            cols[0][row] = re;
+          }
+          for (int t = 0; t < nsl; t++) {
+            F acc = prev;
+            for (int i = t * deg; i < std::min(slots, (t + 1) * deg); i++) {
+              F combo = real_wvals[stride * i][row] + ld.lookup_A * real_wvals[stride * i + 1][row];
+              F term = inv(ld.lookup_alpha - combo);
+              acc = table ? acc + real_wvals[3 * i + 2][row] * term : acc - term;
+            }
+            cols[1 + t][row] = acc;
+            prev = acc;
+          }
+        }
+        if (prev != F(0) && !bad_lookup) { fprintf(stderr, "[prover] lookup sums do not cancel\n"); exit(8); }
+        for (auto &col : cols) pp_cols.push_back(intt(col, n));
+      }
+    }
   }
   commitOracle(2);
   proof.plonk_zs_partial_products_cap = trees[2].cap();
@@ -664,6 +766,11 @@ static ProverOut prove(const Preset &p, const CommonCircuitData &c, u64 seed, in
           int inext = (i + (M >> n)) % M;  // omega * x_i = x_{i + M/N}
           for (int t = 0; t < r; t++) { fo.plonk_zs.push_back(fromBase(lde[2][t][i])); fo.plonk_zs_next.push_back(fromBase(lde[2][t][inext])); }
           for (int t = 0; t < r * c.num_partial_products; t++) fo.partial_products.push_back(fromBase(lde[2][r + t][i]));
+          for (int t = 0; t < r * c.num_lookup_polys; t++) {
+            size_t col = (size_t)r * (1 + c.num_partial_products) + t;
+            fo.lookup_zs.push_back(fromBase(lde[2][col][i]));
+            fo.lookup_zs_next.push_back(fromBase(lde[2][col][inext]));
+          }
           ProofChallenges ch = pch;
           ch.plonk_zeta = fromBase(xs[i]);
           std::vector<FExt> cj = evalCombinedPlonkConstraints(c, fake, ch);
@@ -938,19 +1045,20 @@ static std::string proofJson(const ProofWithPublicInputs &pw) {
 
 int main(int argc, char **argv) {
   if (argc < 3) {
-    fprintf(stderr, "usage: p2v_prover <preset> <out_prefix> [--seed K] [--corrupt-layer S] [--bad-final] [--bad-witness ROW] [--bad-copy] [--threads T]\n");
+    fprintf(stderr, "usage: p2v_prover <preset> <out_prefix> [--seed K] [--corrupt-layer S] [--bad-final] [--bad-witness ROW] [--bad-copy] [--bad-lookup] [--threads T]\n");
     return 2;
   }
   std::string preset = argv[1], prefix = argv[2];
   u64 seed = 1;
   int corrupt_layer = -1, bad_witness_row = -1, threads = (int)std::thread::hardware_concurrency();
-  bool bad_final = false, bad_copy = false;
+  bool bad_final = false, bad_copy = false, bad_lookup = false;
   for (int i = 3; i < argc; i++) {
     std::string a = argv[i];
     if (a == "--seed" && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 10);
     else if (a == "--corrupt-layer" && i + 1 < argc) corrupt_layer = atoi(argv[++i]);
     else if (a == "--bad-final") bad_final = true;
     else if (a == "--bad-copy") bad_copy = true;
+    else if (a == "--bad-lookup") bad_lookup = true;
     else if (a == "--bad-witness" && i + 1 < argc) bad_witness_row = atoi(argv[++i]);
     else if (a == "--threads" && i + 1 < argc) threads = atoi(argv[++i]);
     else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
@@ -959,7 +1067,7 @@ int main(int argc, char **argv) {
   activePermutation() = permutationBulk;  // bit-identical to `permutation` (tests/test_oracle.py)
   Preset p = makePreset(preset);
   CommonCircuitData c = toCommon(p);
-  ProverOut out = prove(p, c, seed, corrupt_layer, bad_final, threads, bad_witness_row, bad_copy);
+  ProverOut out = prove(p, c, seed, corrupt_layer, bad_final, threads, bad_witness_row, bad_copy, bad_lookup);
   // self-check with the verifier restatement (dense-MDS permutation)
   activePermutation() = permutation;
   permCounter() = 0;

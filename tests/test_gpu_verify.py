@@ -32,7 +32,8 @@ def test_fixture_accepts_and_intermediates_match(p2v, ctx, orc, name):
 
 
 @pytest.mark.parametrize("name,code", [("small6_badfinal", 3), ("small6_badlayer0", 18), ("small6_badlayer1", 18 | (1 << 16)),
-                                       ("real5_badwitness", 1 | (3 << 16)), ("real5_badcopy", 1 | (3 << 16))])
+                                       ("real5_badwitness", 1 | (3 << 16)), ("real5_badcopy", 1 | (3 << 16)),
+                                       ("reallu6_badlookup", 1 | (3 << 16))])
 def test_regrinded_rejections(p2v, ctx, orc, name, code):
     """Proofs that reach the deep checks (need prover-side re-grinding): FALSE_FINAL, ERR_STEP_EVAL."""
     cir, shape, lay, vkey, blob = _circuit(p2v, ctx, name)

@@ -126,7 +126,8 @@ def test_s12_permutation_count(orc):
 
 
 @pytest.mark.parametrize("name,code", [("small6_badfinal", 3), ("small6_badlayer0", 18), ("small6_badlayer1", 18 | (1 << 16)),
-                                       ("real5_badwitness", 1 | (3 << 16)), ("real5_badcopy", 1 | (3 << 16))])
+                                       ("real5_badwitness", 1 | (3 << 16)), ("real5_badcopy", 1 | (3 << 16)),
+                                       ("reallu6_badlookup", 1 | (3 << 16))])
 def test_regrinded_rejections(orc, name, code):
     shape, lay, vkey, blob = fixtures.load(name)
     res = orc.verify_batch(shape, vkey, blob, threads=1, fast=False)

@@ -54,7 +54,7 @@ def test_python_twin_kat():
 
 
 @pytest.mark.parametrize("name", ["small6", "fixed4", "arity5", "lookup6", "mid5", "small6_badfinal", "small6_badlayer0", "small6_badlayer1",
-                                  "real5", "real5_badwitness", "real5_badcopy"])
+                                  "real5", "real5_badwitness", "real5_badcopy", "reallu6", "reallu6_badlookup"])
 def test_twins_agree_on_fixtures(orc, name):
     shape, lay, vkey, blob = fixtures.load(name)
     common, vk, proof = pyref.load_fixture(fixtures.GOLDEN, name, fixtures.REJECTING.get(name))
