@@ -305,7 +305,7 @@ __device__ __forceinline__ u64 poseidon_crt_fold(double T, u32 Th) {
   u32 r0, r1;
   asm("{\n\t.reg .u32 t,w2,c;\n\t"
       "shl.b32 t,%4,10;\n\tadd.cc.u32 %1,%3,t;\n\t"          // w1 = Lh + ((Th/2) << 11)
-      "shr.u32 w2,%4,22;\n\taddc.u32 w2,w2,0;\n\t"           // w2 = ((Th/2) >> 21) + carry
+      "shf.l.clamp.b32 w2,%4,0,10;\n\taddc.u32 w2,w2,0;\n\t" // w2 = ((Th/2) >> 21) + carry  (funnel shift: keeps ptxas from fusing the pair into an IMAD.WIDE by 1024)
       "add.cc.u32 %1,%1,w2;\n\taddc.u32 c,0,0;\n\t"
       "add.u32 w2,w2,c;\n\tadd.u32 %1,%1,c;\n\t"
       "sub.cc.u32 %0,%2,w2;\n\tsubc.u32 %1,%1,0;\n\t}"
