@@ -249,6 +249,9 @@ struct TracePoint { const char *what; int chunk; size_t m; cudaEvent_t ev; };
 #define P2V_RAMP_NUM 9
 #define P2V_RAMP_DEN 8
 #endif
+#ifndef P2V_RAMP_START_DIV
+#define P2V_RAMP_START_DIV 8
+#endif
 int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t n, int what, Outputs out) {
   auto host_t0 = std::chrono::steady_clock::now();
   auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
@@ -316,7 +319,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   // Measured at 10^5 S12 proofs from pinned memory (tools/ramp_sweep.sh): x2 292k, x1.5 296k, x1.25 300k,
   // x1.125 319k, x1.0625 313k proofs/s; constant chunks of 2-8 k proofs 238k-308k.
   // (Measured: ramping device-resident input only adds launches.)
-  size_t ramp = (!src_dev && depth == 2 && chunk >= 8 * 1024) ? chunk / 8 / 32 * 32 : chunk;
+  size_t ramp = (!src_dev && depth == 2 && chunk >= 8 * 1024) ? chunk / P2V_RAMP_START_DIV / 32 * 32 : chunk;
   for (size_t c0 = 0, m = 0; c0 < n; c0 += m, k++) {
     m = std::min(ramp, n - c0);
     ramp = std::min(chunk, (ramp * P2V_RAMP_NUM / P2V_RAMP_DEN + 31) / 32 * 32);
