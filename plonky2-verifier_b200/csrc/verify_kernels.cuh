@@ -270,9 +270,11 @@ __global__ void __launch_bounds__(128) k_challenges(const __grid_constant__ DevC
 // Thread t = (tree, q, proof), tree-major so that a warp works on one tree: trees 0..3 are the
 // initial oracles (leaf = row of the oracle, path to the cap), trees 4.. are the commit-phase
 // trees (leaf = flattened coset evals).  ~97% of all permutations of a verification run here,
-// through a single permutation call site.
+// through a single permutation call site.  3 blocks of 256 per SM (80 registers, no spills, 6 warps per scheduler)
+// measured 2% faster than 4 blocks (64 registers, 112 bytes of spills around the permutation, 8 warps): the pipes,
+// not the latency, are the limit.
 #ifndef P2V_MERKLE_MINBLOCKS
-#define P2V_MERKLE_MINBLOCKS 4
+#define P2V_MERKLE_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(256, P2V_MERKLE_MINBLOCKS) k_fri_merkle(const __grid_constant__ DevCircuit c, Workspace ws, size_t n) {
   const int Q = c.Q;
