@@ -270,11 +270,12 @@ __global__ void __launch_bounds__(128) k_challenges(const __grid_constant__ DevC
 // Thread t = (tree, q, proof), tree-major so that a warp works on one tree: trees 0..3 are the
 // initial oracles (leaf = row of the oracle, path to the cap), trees 4.. are the commit-phase
 // trees (leaf = flattened coset evals).  ~97% of all permutations of a verification run here,
-// through a single permutation call site.  3 blocks of 256 per SM (80 registers, no spills, 6 warps per scheduler)
-// measured 2% faster than 4 blocks (64 registers, 112 bytes of spills around the permutation, 8 warps): the pipes,
-// not the latency, are the limit.
+// through a single permutation call site.  Occupancy: the pipes, not latency, are the limit, and ptxas needs
+// registers more than the SM needs warps — measured on 5x10^4 S12 proofs (fraction of the integer-pipe roofline):
+// 4 blocks of 256 per SM (64 registers, 112 B of spills, 8 warps/scheduler) 79.5%, 3 blocks (80 registers) 82.2%,
+// 2 blocks (115 registers, no spills, 4 warps/scheduler) 83.9%.
 #ifndef P2V_MERKLE_MINBLOCKS
-#define P2V_MERKLE_MINBLOCKS 3
+#define P2V_MERKLE_MINBLOCKS 2
 #endif
 __global__ void __launch_bounds__(256, P2V_MERKLE_MINBLOCKS) k_fri_merkle(const __grid_constant__ DevCircuit c, Workspace ws, size_t n) {
   const int Q = c.Q;
