@@ -268,9 +268,10 @@ int p2v_verify_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, 
                      uint32_t *accept_bits, uint32_t *status);
 /* Limit on proofs staged per pass (SoA workspace = chunk * blob_words * 8 bytes); 0 = default. */
 int p2v_ctx_set_chunk(p2v_ctx *ctx, size_t proofs_per_chunk);
-/* Chunk pipelining: depth 2 (default) runs consecutive chunks on two streams with two workspaces, so the
- * per-proof kernels (K0, K4, K5) of chunk k+1 overlap the Merkle kernel of chunk k; depth 1 is strictly serial
- * and is the mode in which p2v_ctx_last_ms is meaningful.  Results are identical. */
+/* Chunk pipelining: depth 2..4 (default 3) runs consecutive chunks round-robin on that many streams and
+ * workspaces, so the latency-bound per-proof kernels (K0, K4, K5) of the next chunk(s) overlap the Merkle kernel of
+ * the current one; depth 1 is strictly serial and is the mode in which p2v_ctx_last_ms is meaningful.
+ * Results are identical. */
 int p2v_ctx_set_pipeline(p2v_ctx *ctx, int depth);
 
 /* Synthetic batches (north_star: "synthetic batches built from the bundled JSON proofs"):

@@ -8,16 +8,21 @@
 #include <vector>
 #include "../../include/p2v.h"
 
+#define P2V_MAX_DEPTH 4
+
 struct p2v_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
-  cudaStream_t stream2 = nullptr;  // second compute stream: chunk k+1's K0/K4/K5 overlap chunk k's K6
-  int pipeline = 2;                // 1 = strictly serial chunks (per-section timings valid), 2 = overlapped
-  void *ws2 = nullptr;
-  size_t ws2_bytes = 0;
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  // chunk pipeline: lane 0 is `stream` + `ws`; lanes 1.. have their own stream and workspace, so the latency-bound
+  // per-proof kernels (K0, K4, K5) of the next chunks run under the Merkle kernel of the current one
+  cudaStream_t lane_stream[P2V_MAX_DEPTH] = {};  // [0] unused (= stream)
+  void *lane_ws[P2V_MAX_DEPTH] = {};             // [0] unused (= ws)
+  size_t lane_ws_bytes[P2V_MAX_DEPTH] = {};
+  cudaEvent_t lane_join[P2V_MAX_DEPTH] = {};
+  int pipeline = 3;                // 1 = strictly serial chunks (per-section timings valid), 2..P2V_MAX_DEPTH = overlapped
+  cudaEvent_t fork_ev = nullptr;
   std::string err;
   uint64_t launches = 0;
   size_t chunk = 0;  // proofs per pass; 0 = default

@@ -30,9 +30,11 @@ int p2v_ctx_create(int device, p2v_ctx **out) {
   ctx->sm_count = prop.multiProcessorCount;
   P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  for (int i = 1; i < P2V_MAX_DEPTH; i++) {
+    P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->lane_stream[i], cudaStreamNonBlocking));
+    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->lane_join[i], cudaEventDisableTiming));
+  }
   P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
-  P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
   for (auto &ev : ctx->ev) P2V_CUDA(nullptr, cudaEventCreate(&ev));
   for (int i = 0; i < 2; i++) {
     P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming));
@@ -57,13 +59,15 @@ void p2v_ctx_destroy(p2v_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
-  cudaStreamSynchronize(ctx->stream2);
+  for (int i = 1; i < P2V_MAX_DEPTH; i++) cudaStreamSynchronize(ctx->lane_stream[i]);
   if (ctx->ws) cudaFree(ctx->ws);
-  if (ctx->ws2) cudaFree(ctx->ws2);
+  for (int i = 1; i < P2V_MAX_DEPTH; i++) {
+    if (ctx->lane_ws[i]) cudaFree(ctx->lane_ws[i]);
+    if (ctx->lane_join[i]) cudaEventDestroy(ctx->lane_join[i]);
+    cudaStreamDestroy(ctx->lane_stream[i]);
+  }
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
-  if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
-  cudaStreamDestroy(ctx->stream2);
   for (auto &b : ctx->stage_buf)
     if (b) cudaFree(b);
   for (auto &ev : ctx->ev)
@@ -88,7 +92,7 @@ int p2v_ctx_sync(p2v_ctx *ctx) {
 uint64_t p2v_ctx_launch_count(const p2v_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int p2v_ctx_set_pipeline(p2v_ctx *ctx, int depth) {
-  if (!ctx || depth < 1 || depth > 2) return p2v_fail(ctx, P2V_E_INVALID, "p2v_ctx_set_pipeline: depth must be 1 or 2");
+  if (!ctx || depth < 1 || depth > P2V_MAX_DEPTH) return p2v_fail(ctx, P2V_E_INVALID, "p2v_ctx_set_pipeline: depth must be 1.." + std::to_string(P2V_MAX_DEPTH));
   ctx->pipeline = depth;
   return P2V_OK;
 }

@@ -149,12 +149,12 @@ size_t carve(const DevCircuit &d, size_t m, char *base, Workspace *ws, bool want
 }
 
 int ensureWorkspace(p2v_ctx *ctx, int which, size_t bytes) {
-  void *&ws = which ? ctx->ws2 : ctx->ws;
-  size_t &have = which ? ctx->ws2_bytes : ctx->ws_bytes;
+  void *&ws = which == 0 ? ctx->ws : ctx->lane_ws[which];
+  size_t &have = which == 0 ? ctx->ws_bytes : ctx->lane_ws_bytes[which];
   if (have >= bytes) return P2V_OK;
   if (ws) {
     P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
+    for (int i = 1; i < P2V_MAX_DEPTH; i++) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->lane_stream[i]));
     cudaFree(ws);
     ws = nullptr;
     have = 0;
@@ -262,25 +262,28 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   const DevCircuit &d = cir->dev;
   const size_t blob_words = (size_t)d.L.blob_words;
   bool src_dev = p2v_is_device_ptr(blobs);
-  // Chunking.  Serial mode: as few chunks as memory allows.  Pipelined mode (default): ~2 GiB chunks on two
-  // streams / two workspaces, so K0+K4+K5 of chunk k+1 (latency-bound, one thread per proof) fill the GPU
-  // next to the Merkle kernel of chunk k, and (host input) the H2D copy of chunk k+1 runs under chunk k.
+  // Chunking.  Serial mode: as few chunks as memory allows.  Pipelined mode (default): chunks go round-robin over
+  // `pipeline` lanes (stream + workspace each), so K0+K4+K5 of the next chunks (latency-bound, one thread per proof)
+  // fill the GPU next to the Merkle kernel of the current one.  Device-resident input: ~2 GiB chunks.  Host input:
+  // ~0.5 GiB chunks — a chunk cannot start before it has arrived, PCIe delivers proofs only ~1.1x faster than the
+  // GPU verifies them, so there is never a backlog of big chunks to overlap; small constant chunks on 3 lanes
+  // measured 370 k proofs/s end to end against 348 k for 2 GiB chunks behind a ramp (tools/chunk_sweep.sh).
   size_t chunk = ctx->chunk;
   if (chunk == 0) {
-    size_t budget = ctx->pipeline > 1 ? ((size_t)2 << 30) : (src_dev ? ((size_t)16 << 30) : ((size_t)2 << 30));
+    size_t budget = ctx->pipeline > 1 ? (src_dev ? ((size_t)2 << 30) : ((size_t)512 << 20)) : (src_dev ? ((size_t)16 << 30) : ((size_t)2 << 30));
     chunk = budget / (blob_words * 8);
     if (chunk < 1024) chunk = 1024;
   }
   chunk = (chunk + 31) / 32 * 32;
   if (chunk > n) chunk = (n + 31) / 32 * 32;
-  const int depth = (ctx->pipeline > 1 && n > chunk) ? 2 : 1;
+  const int depth = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->pipeline, (n + chunk - 1) / chunk));
   bool want_folded = out.folded != nullptr;
   size_t ws_bytes = carve(d, chunk, nullptr, nullptr, want_folded);
   int rc;
-  Workspace wsp[2];
+  Workspace wsp[P2V_MAX_DEPTH];
   for (int k = 0; k < depth; k++) {
     if ((rc = ensureWorkspace(ctx, k, ws_bytes))) return rc;
-    carve(d, chunk, (char *)(k ? ctx->ws2 : ctx->ws), &wsp[k], want_folded);
+    carve(d, chunk, (char *)(k == 0 ? ctx->ws : ctx->lane_ws[k]), &wsp[k], want_folded);
   }
   if (!src_dev && (rc = ensureStage(ctx, chunk * blob_words * 8))) return rc;
 
@@ -293,11 +296,13 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   if ((rc = o_bits.init(ctx, out.accept_bits, (n + 31) / 32 * 4))) return rc;
   if ((rc = o_qs.init(ctx, out.qstatus, n * d.Q * 4))) return rc;
   if ((rc = o_folded.init(ctx, out.folded, (size_t)2 * n * d.Q * 8))) return rc;
-  cudaStream_t streams[2] = {ctx->stream, ctx->stream2};
-  if (depth == 2) {
-    // fork: the second stream starts after everything already queued on the primary one
+  cudaStream_t streams[P2V_MAX_DEPTH];
+  streams[0] = ctx->stream;
+  for (int i = 1; i < P2V_MAX_DEPTH; i++) streams[i] = ctx->lane_stream[i];
+  if (depth >= 2) {
+    // fork: the other streams start after everything already queued on the primary one
     P2V_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
-    P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->fork_ev, 0));
+    for (int i = 1; i < depth; i++) P2V_CUDA(ctx, cudaStreamWaitEvent(streams[i], ctx->fork_ev, 0));
   }
   const bool timed = depth == 1;
   static const bool trace_on = getenv("P2V_TRACE") != nullptr;
@@ -319,14 +324,15 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   // Measured at 10^5 S12 proofs from pinned memory (tools/ramp_sweep.sh): x2 292k, x1.5 296k, x1.25 300k,
   // x1.125 319k, x1.0625 313k proofs/s; constant chunks of 2-8 k proofs 238k-308k.
   // (Measured: ramping device-resident input only adds launches.)
-  size_t ramp = (!src_dev && depth == 2 && chunk >= 8 * 1024) ? chunk / P2V_RAMP_START_DIV / 32 * 32 : chunk;
+  size_t ramp = (!src_dev && depth >= 2 && chunk >= 8 * 1024) ? chunk / P2V_RAMP_START_DIV / 32 * 32 : chunk;
   for (size_t c0 = 0, m = 0; c0 < n; c0 += m, k++) {
     m = std::min(ramp, n - c0);
     ramp = std::min(chunk, (ramp * P2V_RAMP_NUM / P2V_RAMP_DEN + 31) / 32 * 32);
     const u64 *src = blobs + c0 * blob_words;
-    int b = k & 1;
-    cudaStream_t st = streams[depth == 2 ? b : 0];
-    Workspace &ws = wsp[depth == 2 ? b : 0];
+    int b = k & 1;              // staging buffer (host input): two of them, released by K0
+    int lane = k % depth;       // stream + workspace of this chunk
+    cudaStream_t st = streams[lane];
+    Workspace &ws = wsp[lane];
     if (!src_dev) {
       // double-buffered staging: the H2D copy of chunk k+1 overlaps the kernels of chunk k; buffer b is free
       // again once the K0 that read it (chunk k-2) has finished
@@ -360,7 +366,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
       size_t items = m * (size_t)d.Q * (4 + d.nsteps);
       // serial mode: persistent grid; pipelined mode: one block per 256 openings, so that blocks of the two
       // streams' kernels interleave on the SMs as resources free up
-      unsigned grid = depth == 2 ? (unsigned)((items + 255) / 256) : (unsigned)p2v_grid_for(ctx, items, 256, P2V_MERKLE_MINBLOCKS);
+      unsigned grid = depth >= 2 ? (unsigned)((items + 255) / 256) : (unsigned)p2v_grid_for(ctx, items, 256, P2V_MERKLE_MINBLOCKS);
       P2V_LAUNCH_ON(ctx, st, k_fri_merkle, grid, 256, 0, d, ws, m);
       if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
       P2V_LAUNCH_ON(ctx, st, k_fri_query, p2v_grid_for(ctx, m * d.Q, 256, 4), 256, 0, d, ws, m);
@@ -381,10 +387,12 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     if (o_qs.dev) P2V_LAUNCH_ON(ctx, st, k_copy_qstat, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.qstat, m, d.Q, o_qs.as<u32>(), c0);
     if (o_folded.dev) P2V_LAUNCH_ON(ctx, st, k_copy_folded, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.folded, m, d.Q, o_folded.as<u64>(), n, c0);
   }
-  if (depth == 2) {
-    // join: whoever orders work after us on the primary stream (D2H below, the caller's events, NCCL) sees both
-    P2V_CUDA(ctx, cudaEventRecord(ctx->join_ev, ctx->stream2));
-    P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
+  if (depth >= 2) {
+    // join: whoever orders work after us on the primary stream (D2H below, the caller's events, NCCL) sees all lanes
+    for (int i = 1; i < depth; i++) {
+      P2V_CUDA(ctx, cudaEventRecord(ctx->lane_join[i], streams[i]));
+      P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane_join[i], 0));
+    }
   }
   double host_issued = host_ms();
   bool any_host = false;

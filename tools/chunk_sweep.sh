@@ -1,7 +1,5 @@
 #!/bin/sh
-for c in 1536 2048 3072 4096 6144 8160; do
-  echo "== chunk $c"; python tools/e2e_probe.py 100000 $c 2>&1 | tail -7 | head -4
-done
-P2V_EXTRA_NVCC="-DP2V_RAMP_NUM=17 -DP2V_RAMP_DEN=16" python plonky2-verifier_b200/build.py > /dev/null 2>&1
-echo "== ramp 17/16"; python tools/e2e_probe.py 100000 2>&1 | tail -7 | head -4
-python plonky2-verifier_b200/build.py > /dev/null 2>&1
+# host-buffer (e2e) throughput for constant chunk sizes (no ramp below 8192) x pipeline depth
+for c in 2048 3072 4096 6144; do for d in 3 4; do
+  printf "chunk %s depth %s: " $c $d; python tools/e2e_probe.py 100000 $c $d 2>&1 | grep "^step" | tail -3 | awk '{s+=$5} END {print s/3, "proofs/s"}'
+done; done

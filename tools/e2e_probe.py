@@ -8,6 +8,8 @@ shape, lay, vkey, blob = fixtures.load("s12")
 ctx = p2v.Context(0); cir = p2v.Circuit(ctx, shape, vkey)
 if len(sys.argv) > 2:
     ctx.set_chunk(int(sys.argv[2]))
+if len(sys.argv) > 3:
+    ctx.set_pipeline(int(sys.argv[3]))
 W = lay.blob_words
 h = torch.empty((n, W), dtype=torch.int64, pin_memory=True)
 hb = h.numpy().view(np.uint64); hb[:] = blob
