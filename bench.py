@@ -241,13 +241,13 @@ def main():
     launches = ctx.launch_count - launches0
     ms_total = e0.elapsed_time(e1)
     # per-kernel device times: one extra pass in strictly serial mode (one chunk, one stream), outside the timed
-    # region; the timed region above runs the default two-stream chunk pipeline where kernels overlap
+    # region; the timed region above runs the default multi-lane chunk pipeline where kernels overlap
     ctx.set_pipeline(1)
     step_device()
     ctx.sync()
     fri_ms = ctx.last_ms("fri_merkle")
     sec_ms = {k: ctx.last_ms(k) for k in ("stage", "challenges", "constraints", "fri", "fri_merkle", "verdict")}
-    ctx.set_pipeline(2)
+    ctx.set_pipeline(p2v.DEFAULT_PIPELINE)
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

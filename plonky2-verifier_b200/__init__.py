@@ -264,6 +264,9 @@ def parse_proofs(json_texts, shape, threads=0, out=None, return_codes=False):
 
 # ---- GPU context -------------------------------------------------------------------------------
 
+DEFAULT_PIPELINE = 3  # lanes of the chunk pipeline a new context starts with (p2v_ctx_set_pipeline)
+
+
 class Context:
     """One GPU, one stream.  All methods run on the GPU through the C ABI."""
 

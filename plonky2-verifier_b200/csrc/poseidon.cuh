@@ -6,16 +6,18 @@
 //   M[i][j] = circ[(j-i) mod 12] + (i==j ? diag[i] : 0),  circ = (17,15,41,16,2,28,13,13,39,18,34,20), diag = (8,0,...)
 // (mdsMatrixCoeff, src/Hash/Constants.hs:21-25; linearDiffusion, Hash/Poseidon.hs:100-101).
 //
-// Why the DENSE layer in every round and not Plonky2's fast-partial-round tables, and why 22-bit
-// limbs: measured on B200 (p2v_int_pipe_peak), IMAD.WIDE.U32 issues every 4 cycles per SM
-// sub-partition, a 32-bit IMAD every 2 (like an ALU op).  A 64x64 mulmod needs 4 IMAD.WIDE + ~16
-// other instructions, so the 22 mulmods per round of the "fast" partial form cost far more FMA-pipe
-// time than a dense layer made of plain 32-bit IMADs: the state is cut into 22/22/20-bit limbs,
-// each limb column is accumulated with `IMAD acc = limb*coeff + acc` (row sum 264 keeps every
-// accumulator below 2^31: no carries, no IMAD.WIDE), and the three accumulators of an output are
-// recombined with one reduction.  ptxas turns the x16 / x2 coefficients into LEA on the ALU pipe by
-// itself, which balances the two pipes.  The fast-partial tables are still used by the
-// PoseidonGate constraint program (constraints.cuh), as in the reference.
+// Why the DENSE layer in every round and not Plonky2's fast-partial-round tables: measured on B200
+// (p2v_int_pipe_peak), IMAD.WIDE.U32 issues every 4 cycles per SM sub-partition, a 32-bit IMAD every 2 (like an
+// ALU op), a DFMA every 2 on a pipe of its own.  A 64x64 mulmod needs 4 IMAD.WIDE + ~13 other instructions, so the
+// 22 mulmods per round of the "fast" partial form cost far more FMA-pipe time than a dense layer made of
+// small-constant multiply-adds that never need a wide multiply.  Three generations of that layer live here, all
+// bit-exact (tests/test_gpu_hash.py), selected by POSEIDON_MDS_F64:
+//   0  poseidon_mds        22/22/20-bit limbs, 3 x 144 carry-free 32-bit IMADs
+//   1  poseidon_mds_f64    32-bit halves as doubles, 2 x 144 exact DFMAs (the FP64 pipe is otherwise idle)
+//   2  poseidon_mds_mixed  low 43 bits: 144 DFMAs, high 21 bits: 144 IMADs (two pipes)
+//   3  poseidon_mds_crt    (default) the same split after a CRT step on the circulant: 2 x 72 multiply-adds
+// The fast-partial tables are still used by the PoseidonGate constraint program (constraints.cuh), as in the
+// reference.
 //
 // Round constants are folded into the accumulators of the preceding linear layer.
 #pragma once

@@ -87,11 +87,12 @@ def test_chunked_and_device_resident(p2v, ctx, orc):
     blobs, words, deltas = fixtures.tampered_batch(blob, lay, shape, n, seed=3)
     acc0, st0 = cir.verifyProof(blobs)
     ctx.set_chunk(64)
-    acc1, st1 = cir.verifyProof(blobs)       # 4 chunks on the two-stream pipeline (default depth 2)
-    ctx.set_pipeline(1)
-    acc3, st3 = cir.verifyProof(blobs)       # same chunks, strictly serial
-    ctx.set_pipeline(2)
-    assert np.array_equal(st1, st3) and np.array_equal(acc1, acc3)
+    acc1, st1 = cir.verifyProof(blobs)       # 4 chunks on the multi-lane pipeline (default depth 3)
+    for depth in (1, 2, 4):                  # strictly serial, two lanes, four lanes
+        ctx.set_pipeline(depth)
+        acc3, st3 = cir.verifyProof(blobs)
+        assert np.array_equal(st1, st3) and np.array_equal(acc1, acc3), depth
+    ctx.set_pipeline(p2v.DEFAULT_PIPELINE)
     ch_p = cir.proofChallenges(blobs)        # debug outputs gathered across pipelined chunks
     st_p, qs_p, fold_p = cir.checkFRIProof(blobs, want_debug=True)
     d_blobs = torch.from_numpy(blobs.view(np.int64)).cuda()
@@ -131,7 +132,7 @@ def test_ragged_batch_sizes(p2v, ctx, orc, n):
 
 
 def test_host_ramped_pipeline_equals_device_resident(p2v, ctx, orc):
-    """Host input with chunks >= 8192 takes the ramped two-stream pipeline (chunk/8 growing x9/8): every proof must
+    """Host input with chunks >= 8192 takes the ramped multi-lane pipeline (chunk/8 growing x9/8): every proof must
     land in exactly one chunk.  Compared with the device-resident run of the same batch and, on a sample, the oracle."""
     import torch
 
