@@ -262,6 +262,26 @@ def parse_proofs(json_texts, shape, threads=0, out=None, return_codes=False):
     return out
 
 
+class pinned_u64:
+    """Context manager: a page-locked u64 host array from p2v_host_alloc (what the chunk pipeline copies from at
+    full PCIe rate), released on exit."""
+
+    def __init__(self, words):
+        self.words = int(words)
+        self._p = C.c_void_p()
+
+    def __enter__(self):
+        rc = lib().p2v_host_alloc(max(self.words, 1) * 8, C.byref(self._p))
+        if rc:
+            raise P2VError(rc, lib().p2v_last_error(None).decode())
+        return np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint64)), shape=(self.words,))
+
+    def __exit__(self, *exc):
+        lib().p2v_host_free(self._p)
+        self._p = C.c_void_p()
+        return False
+
+
 # ---- GPU context -------------------------------------------------------------------------------
 
 DEFAULT_PIPELINE = 3  # lanes of the chunk pipeline a new context starts with (p2v_ctx_set_pipeline)
@@ -454,6 +474,21 @@ class Circuit:
             status = np.empty(n, dtype=np.uint32)
         self.ctx._check(lib().p2v_verify_batch(self.ctx._h, self._h, _ptr(blobs), n, _ptr(accept_bits), _ptr(status)))
         return (unpack_bits(accept_bits, n), status) if host else (accept_bits, status)
+
+    def verifyProofJson(self, json_texts, threads=0):
+        """What `testmain` does for one proof (src/testmain.hs:31-63), for a batch: decode the `*_proof.json` texts on
+        `threads` host threads straight into pinned memory, verify on the GPU -> (accept bool[n], status u32[n],
+        decode_rc i32[n]).  A text that does not decode (or does not match the circuit's shape) is reported in decode_rc and
+        counted as rejected; it does not stop the batch."""
+        n = len(json_texts)
+        lay = self.layout
+        if n == 0:
+            return np.zeros(0, dtype=bool), np.zeros(0, dtype=np.uint32), np.zeros(0, dtype=np.int32)
+        with pinned_u64(n * lay.blob_words) as buf:
+            blobs, rcs = parse_proofs(json_texts, self.shape, threads=threads, out=buf.reshape(n, lay.blob_words), return_codes=True)
+            accept, status = self.verifyProof(blobs, n=n)
+        accept = accept & (rcs == 0)
+        return accept, status, rcs
 
     def synth_batch(self, template_blob, n, tamper_word, tamper_delta, blobs_out):
         """Replicate + tamper a template into a device AoS batch (synthetic inputs)."""

@@ -153,3 +153,22 @@ def test_host_ramped_pipeline_equals_device_resident(p2v, ctx, orc):
     want = orc.verify_batch(shape, vkey, blobs[sample], threads=4, fast=True)
     assert np.array_equal(st_h[sample], want["status"])
     assert acc_h[words < 0].all()
+
+
+def test_json_in_verdict_out(p2v, ctx, orc):
+    """The reference's testmain flow for a batch: JSON texts -> threaded decode into pinned memory -> GPU verdicts.
+    A text that does not decode is reported and rejected without stopping the others."""
+    import json
+
+    cir, shape, lay, vkey, blob = _circuit(p2v, ctx, "small6")
+    good = fixtures.read("small6", "proof")
+    texts = [good, fixtures.read("small6_badfinal", "proof"), good, "{ not json", fixtures.read("small6_badlayer1", "proof")]
+    bad = json.loads(good)
+    bad["proof"]["openings"]["wires"].pop()
+    texts.append(json.dumps(bad))
+    accept, status, rcs = cir.verifyProofJson(texts, threads=3)
+    assert list(rcs) == [0, 0, 0, -4, 0, -5]
+    assert list(accept) == [True, False, True, False, False, False]
+    assert [int(s) for s in status[[0, 1, 2, 4]]] == [0, 3, 0, 18 | (1 << 16)]
+    a0, s0, r0 = cir.verifyProofJson([])
+    assert a0.size == 0 and s0.size == 0 and r0.size == 0
