@@ -26,7 +26,8 @@
 //   p2v_prover <preset> <out_prefix> [--seed K] [--corrupt-layer S] [--bad-final] [--bad-witness ROW] [--bad-copy] [--bad-lookup]
 //
 // Presets: s12 (standard recursion shape), mid5, small6, fixed4, arity5, lookup6 (all-Noop rows, quotient == 0);
-//          real5, real7 (ACTIVE gates of all 14 standard kinds on honest witnesses, real quotient C/Z_H),
+//          real5, real7, real12 (ACTIVE gates of all 14 standard kinds on honest witnesses, real quotient C/Z_H;
+//          real12 = the standard recursion configuration, 2^12 rows),
 //          reallu6 (real circuit with an honest lookup argument).
 #include <chrono>
 #include <cstdio>
@@ -224,14 +225,17 @@ static Preset makePreset(const std::string &name) {
     p.gates = {gNoop(), gConst(2), gPI(), gBaseSum(63, 2), gRedExt(32), gRed(43), gArithExt(10), gArith(20), gMulExt(13),
                gExp(66), gRA(4, 4, 2), gCoset(4, 6), gPoseidon(), gPoseidonMds()};
     assignGroups(p, {6, 5, 3});
-  } else if (name == "real5" || name == "real7") {
+  } else if (name == "real5" || name == "real7" || name == "real12") {
     // Same gate set as the standard recursion shape, but the rows carry ACTIVE gates on honestly generated
     // witnesses and the quotient polynomial is the real C(X)/Z_H(X).  Selector groups obey Plonky2's degree rule
     // (group size + gate degree <= quotient_degree_factor + 1): {deg<=2} {deg<=4} {RandomAccess, CosetInterp} {Poseidon, PoseidonMds}.
     p.real = true;
-    p.degree_bits = name == "real5" ? 5 : 7;
+    p.degree_bits = name == "real5" ? 5 : name == "real7" ? 7 : 12;
     p.rate_bits = 3; p.cap_height = 2; p.pow_bits = 6; p.num_queries = 6;
     p.arity_bits = 2; p.final_poly_bits = 2;
+    if (name == "real12") {  // the standard recursion configuration itself (like s12), with real rows
+      p.cap_height = 4; p.pow_bits = 16; p.num_queries = 28; p.arity_bits = 4; p.final_poly_bits = 5;
+    }
     p.num_wires = 135; p.num_routed = 80; p.num_public_inputs = 5;
     p.gates = {gNoop(), gConst(2), gPI(), gBaseSum(63, 2), gRedExt(32), gRed(43), gArithExt(10), gArith(20), gMulExt(13),
                gExp(66), gRA(4, 4, 2), gCoset(4, 6), gPoseidon(), gPoseidonMds()};

@@ -7,7 +7,7 @@ import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 P = 0xFFFFFFFF00000001
-ACCEPTING = ["s12", "mid5", "small6", "fixed4", "lookup6", "real5", "reallu6", "arity5"]
+ACCEPTING = ["s12", "mid5", "small6", "fixed4", "lookup6", "real5", "real12", "reallu6", "arity5"]
 REJECTING = {"small6_badfinal": "small6", "small6_badlayer0": "small6", "small6_badlayer1": "small6",
              "real5_badwitness": "real5", "real5_badcopy": "real5", "reallu6_badlookup": "reallu6"}
 

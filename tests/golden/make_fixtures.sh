@@ -16,6 +16,7 @@ $P arity5  $G/arity5  --seed 7   # Fixed [5,1]: a 32-point coset per query
 # real circuit: ACTIVE gates of all 14 standard kinds on honest witnesses, copy constraints (non-identity sigma,
 # real grand product Z + partial products), real quotient polynomial
 $P real5   $G/real5   --seed 6
+$P real12  $G/real12  --seed 12  # the standard recursion configuration (2^12 rows, 28 queries, arity 16) with real rows
 $P reallu6 $G/reallu6 --seed 8   # real circuit with an honest lookup argument (Lookup / LookupTable rows, RE + partial sums)
 # rejecting proofs that need a prover-side change (re-grinding after the change):
 $P small6 $G/small6_badfinal  --seed 3 --bad-final        # -> FALSE_FINAL

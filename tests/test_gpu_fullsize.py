@@ -95,12 +95,14 @@ def test_config3_fri_batch_10k(p2v, ctx, orc):
     assert {0, 2, 16, 17} <= codes
 
 
-def test_config4_full_verifier_large_batch(p2v, ctx, orc):
-    """Full verifier on 20 000 S12 proofs resident in HBM, in one chunk and in 3 chunks: identical verdicts,
-    accept bit == (status == 0), periodic in the tamper schedule, sample checked by the oracle."""
+@pytest.mark.parametrize("name", ["s12", "real12"])
+def test_config4_full_verifier_large_batch(p2v, ctx, orc, name):
+    """Full verifier on 20 000 standard-recursion-configuration proofs resident in HBM (the all-Noop fixture and the one
+    with real rows), in one chunk and in 3 chunks: identical verdicts, accept bit == (status == 0), periodic in the
+    tamper schedule, sample checked by the oracle."""
     import torch
 
-    shape, lay, vkey, blob = fixtures.load("s12")
+    shape, lay, vkey, blob = fixtures.load(name)
     cir = p2v.Circuit(ctx, shape, vkey)
     n = 20000
     d_blobs, sched, words_n = _device_batch(p2v, ctx, cir, blob, lay, shape, n, seed=33)

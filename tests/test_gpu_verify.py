@@ -50,7 +50,8 @@ def test_regrinded_rejections(p2v, ctx, orc, name, code):
     assert np.array_equal(folded[:, done], want["folded"][:, done])
 
 
-@pytest.mark.parametrize("name,n", [("small6", 96), ("fixed4", 80), ("lookup6", 96), ("mid5", 64), ("s12", 48)])
+@pytest.mark.parametrize("name,n", [("small6", 96), ("fixed4", 80), ("lookup6", 96), ("mid5", 64), ("s12", 48),
+                                    ("real5", 64), ("reallu6", 96), ("real12", 48), ("arity5", 64)])
 def test_tamper_matrix(p2v, ctx, orc, name, n):
     cir, shape, lay, vkey, blob = _circuit(p2v, ctx, name)
     blobs, words, deltas = fixtures.tampered_batch(blob, lay, shape, n, seed=7)
