@@ -123,7 +123,7 @@ def run_reference(args):
     import fixtures
     import plonky2_verifier_b200 as p2v  # host parser only (JSON -> blob); no GPU call is made in this arm
 
-    shape, lay, vkey, blob = fixtures.load("s12")
+    shape, lay, vkey, blob = fixtures.load(args.fixture)
     cores = os.cpu_count() or 1
     per_step = 16 * cores
     blobs, _, _ = fixtures.tampered_batch(blob, lay, shape, per_step, seed=11)
@@ -158,6 +158,9 @@ def main():
     ap.add_argument("--proofs", type=int, default=100000, help="proofs per GPU per step")
     ap.add_argument("--e2e-proofs", type=int, default=0, help="proofs per GPU for the host-buffer measurement (0 = auto)")
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--fixture", default="s12", choices=["s12", "real12"],
+                    help="template proof of the batch: s12 = standard recursion shape, Plonky2's own 3-group selector layout, all-Noop rows; "
+                         "real12 = same configuration with active gates on every row (4 selector groups)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="proofs per staged chunk on the host-buffer path (0 = library default)")
     args = ap.parse_args()
@@ -186,7 +189,7 @@ def main():
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
 
-    shape, lay, vkey, blob = fixtures.load("s12")
+    shape, lay, vkey, blob = fixtures.load(args.fixture)
     ctx = p2v.Context(local_rank)
     cir = p2v.Circuit(ctx, shape, vkey)
     n = args.proofs
@@ -351,7 +354,7 @@ def main():
         "config": {"workload": "full verifier (challenges + constraints + FRI) on standard-recursion-shape (S12) proofs",
                    "proofs_per_gpu": n, "blob_bytes": W * 8, "queries": shape.num_queries, "perms_per_proof": 114 + shape.num_queries * ppq,
                    "l2": "inputs (%.1f GB per step) are far larger than L2" % (n * W * 8 / 1e9),
-                   "batch": "bundled S12 fixture x %d, 3 of 4 copies tampered in one word" % n,
+                   "batch": "bundled %s fixture x %d, 3 of 4 copies tampered in one word" % (args.fixture, n),
                    "verdict_histogram": hist, "host_numa": "process bound to the GPU's NUMA node (%d cpus) for the pinned staging buffers" % len(os.sched_getaffinity(0)), "pipeline": "3 lanes (stream + workspace); chunks of 2 GiB (device-resident input) / 0.5 GiB (host input); K0/K4/K5 of the next chunks overlap K6 of the current one", "multi_gpu": "contiguous slices + NCCL all_gather of the accept bitmap" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * W * 8, "d2h_bytes_per_step": int(h_bits.nbytes + h_status.nbytes),
                 "proofs_per_gpu": n_e2e, "h2d_copy_gbs_measured": h2d_gbs,
