@@ -362,9 +362,9 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "int_pipe", "kernel": "k_fri_merkle", "achieved": achieved / 1e9, "peak": imad_peak / 1e9, "unit": "GIMAD/s",
-                     "frac": achieved / imad_peak, "traffic": 135000.0 * n, "traffic_unit": "bytes per launch",
-                     "traffic_source": "ncu --set full (profiles/r01_k_fri_merkle_ncu.md): dram read+write = 135.0 kB per proof, "
-                                       "1.05x the algorithmic 28 x 536 x 8 B; scaled to this launch",
+                     "frac": achieved / imad_peak, "traffic": 124900.0 * n, "traffic_unit": "bytes per launch",
+                     "traffic_source": "ncu --set full (profiles/r01_k_fri_merkle_ncu.md): dram read+write = 383.7 MB for 3072 proofs = "
+                                       "124.9 kB per proof, 1.04x the algorithmic 28 x 536 x 8 B; scaled to this launch",
                      "algorithmic_bytes": float(shape.num_queries * lay.query_words * 8 * n),
                      "perms_per_s": perms_per_s, "kernel_ms": fri_ms,
                      "peak_source": "IMAD.WIDE.U32 issue rate measured live on this GPU (p2v_int_pipe_peak mode 0: 32/clk/SM, "
