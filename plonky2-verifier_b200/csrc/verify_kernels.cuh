@@ -277,7 +277,10 @@ __global__ void __launch_bounds__(128) k_challenges(const __grid_constant__ DevC
 #ifndef P2V_MERKLE_MINBLOCKS
 #define P2V_MERKLE_MINBLOCKS 2
 #endif
-__global__ void __launch_bounds__(256, P2V_MERKLE_MINBLOCKS) k_fri_merkle(const __grid_constant__ DevCircuit c, Workspace ws, size_t n) {
+#ifndef P2V_MERKLE_BLOCK
+#define P2V_MERKLE_BLOCK 256
+#endif
+__global__ void __launch_bounds__(P2V_MERKLE_BLOCK, P2V_MERKLE_MINBLOCKS) k_fri_merkle(const __grid_constant__ DevCircuit c, Workspace ws, size_t n) {
   const int Q = c.Q;
   const size_t per_tree = n * (size_t)Q;
   const size_t total = per_tree * (size_t)(4 + c.nsteps);
