@@ -266,6 +266,13 @@ int p2v_fri(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n,
  *   accept_bits: ceil(n/32) words; status: [n] (may be NULL). */
 int p2v_verify_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n,
                      uint32_t *accept_bits, uint32_t *status);
+/* Heterogeneous batches: proofs of DIFFERENT circuits (other degree_bits, gate sets, FRI parameters,
+ * lookups ...) grouped by circuit; group g is verified exactly like p2v_verify_batch(ctx, circuits[g], blobs[g],
+ * counts[g], accept_bits[g], status[g]) — `map (uncurry verifyProof)` over (vkey, proof) pairs that do not share a
+ * vkey.  Groups run back to back on the context's pipeline; a kernel launch is shape-homogeneous by construction
+ * (the circuit is a kernel parameter).  Stops at the first group that fails with an error code. */
+int p2v_verify_groups(p2v_ctx *ctx, size_t n_groups, const p2v_circuit *const *circuits, const uint64_t *const *blobs,
+                      const size_t *counts, uint32_t *const *accept_bits, uint32_t *const *status);
 /* Limit on proofs staged per pass (SoA workspace = chunk * blob_words * 8 bytes); 0 = default. */
 int p2v_ctx_set_chunk(p2v_ctx *ctx, size_t proofs_per_chunk);
 /* Chunk pipelining: depth 2..4 (default 3) runs consecutive chunks round-robin on that many streams and

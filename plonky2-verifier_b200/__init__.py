@@ -137,6 +137,7 @@ def lib():
         "p2v_constraints": (C.c_int, [vp, vp, u64p, sz, u64p, u8p]),
         "p2v_fri": (C.c_int, [vp, vp, u64p, sz, u32p, u32p, u64p]),
         "p2v_verify_batch": (C.c_int, [vp, vp, u64p, sz, u32p, u32p]),
+        "p2v_verify_groups": (C.c_int, [vp, sz, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(vp)]),
         "p2v_ctx_set_chunk": (C.c_int, [vp, sz]),
         "p2v_ctx_set_pipeline": (C.c_int, [vp, C.c_int]),
         "p2v_synth_batch": (C.c_int, [vp, vp, u64p, sz, C.c_void_p, u64p, u64p]),
@@ -157,7 +158,7 @@ EXPORTED_SYMBOLS = [
     "p2v_compress", "p2v_merkle_verify", "p2v_merkle_build", "p2v_merkle_open", "p2v_parse_common",
     "p2v_shape_free", "p2v_parse_gate", "p2v_shape_layout", "p2v_challenges_words", "p2v_parse_vkey",
     "p2v_parse_proof", "p2v_parse_proofs", "p2v_circuit_create", "p2v_circuit_destroy", "p2v_challenges", "p2v_constraints",
-    "p2v_fri", "p2v_verify_batch", "p2v_ctx_set_chunk", "p2v_ctx_set_pipeline", "p2v_synth_batch", "p2v_int_pipe_peak", "p2v_ctx_last_ms",
+    "p2v_fri", "p2v_verify_batch", "p2v_verify_groups", "p2v_ctx_set_chunk", "p2v_ctx_set_pipeline", "p2v_synth_batch", "p2v_int_pipe_peak", "p2v_ctx_last_ms",
 ]
 
 
@@ -398,6 +399,19 @@ class Context:
         self._check(lib().p2v_merkle_open(self._h, _ptr(leaves), w, log_n, cap_height, _ptr(digests), _ptr(idx), n,
                                           _ptr(leaves_out), _ptr(sibs_out), _ptr(cap_out)))
         return leaves_out, sibs_out, cap_out
+
+
+def verify_groups(ctx, groups):
+    """Heterogeneous batch: groups = [(Circuit, blobs), ...] with a different circuit per group ->
+    [(accept bool[n_g], status u32[n_g]), ...]  (p2v_verify_groups)."""
+    k = len(groups)
+    ns = [c._n(b, None) for c, b in groups]
+    bits = [np.zeros((n + 31) // 32, dtype=np.uint32) for n in ns]
+    status = [np.empty(n, dtype=np.uint32) for n in ns]
+    arr = lambda ptrs: (C.c_void_p * k)(*ptrs)
+    ctx._check(lib().p2v_verify_groups(ctx._h, k, arr([c._h for c, _ in groups]), arr([_ptr(b) for _, b in groups]),
+                                       (C.c_size_t * k)(*ns), arr([_ptr(x) for x in bits]), arr([_ptr(x) for x in status])))
+    return [(unpack_bits(bits[g], ns[g]), status[g]) for g in range(k)]
 
 
 def unpack_bits(words, n):

@@ -569,6 +569,17 @@ int p2v_verify_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, 
   return runBatch(ctx, c, blobs, n, RUN_CHALLENGES | RUN_CONSTRAINTS | RUN_FRI, o);
 }
 
+int p2v_verify_groups(p2v_ctx *ctx, size_t n_groups, const p2v_circuit *const *circuits, const uint64_t *const *blobs,
+                      const size_t *counts, uint32_t *const *accept_bits, uint32_t *const *status) {
+  if (!ctx || (n_groups && (!circuits || !blobs || !counts || !accept_bits))) return p2v_fail(ctx, P2V_E_INVALID, "p2v_verify_groups: NULL argument");
+  for (size_t g = 0; g < n_groups; g++) {
+    if (counts[g] == 0) continue;
+    int rc = p2v_verify_batch(ctx, circuits[g], blobs[g], counts[g], accept_bits[g], status ? status[g] : nullptr);
+    if (rc != P2V_OK) return rc;
+  }
+  return P2V_OK;
+}
+
 int p2v_synth_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *template_blob, size_t n, const int32_t *tamper_word,
                     const uint64_t *tamper_delta, uint64_t *blobs_out) {
   if (!ctx || !c || !template_blob || !blobs_out) return p2v_fail(ctx, P2V_E_INVALID, "p2v_synth_batch: NULL argument");

@@ -173,3 +173,17 @@ def test_json_in_verdict_out(p2v, ctx, orc):
     assert [int(s) for s in status[[0, 1, 2, 4]]] == [0, 3, 0, 18 | (1 << 16)]
     a0, s0, r0 = cir.verifyProofJson([])
     assert a0.size == 0 and s0.size == 0 and r0.size == 0
+
+
+def test_heterogeneous_groups(p2v, ctx, orc):
+    """Proofs of different circuits (other degree_bits, gate sets, reduction strategies, lookups) in one call."""
+    groups, wants = [], []
+    for name, n in (("small6", 40), ("fixed4", 33), ("reallu6", 21), ("real5", 17)):
+        cir, shape, lay, vkey, blob = _circuit(p2v, ctx, name)
+        blobs, words, deltas = fixtures.tampered_batch(blob, lay, shape, n, seed=5)
+        groups.append((cir, blobs))
+        wants.append(orc.verify_batch(shape, vkey, blobs, threads=4, fast=True)["status"])
+    got = p2v.verify_groups(ctx, groups)
+    for (acc, status), want in zip(got, wants):
+        assert np.array_equal(status, want)
+        assert np.array_equal(acc, want == 0)
