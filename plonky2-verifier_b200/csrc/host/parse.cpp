@@ -6,6 +6,7 @@
 //   p2v_parse_proof   <- FromJSON ProofWithPublicInputs, src/Types.hs:176-279
 //   p2v_shape_layout  <- the flat blob order (include/p2v.h) + oracleWidths, src/Plonk/FRI.hs:56-65
 // No GPU needed here.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -19,6 +20,7 @@
 using namespace p2vhost;
 
 extern thread_local std::string p2v_tls_error;
+static const bool g_no_fast_parse = getenv("P2V_NO_FAST_PARSE") != nullptr;  // force the tape decoder (tests)
 static int fail(int code, const std::string &msg) {
   p2v_tls_error = msg;
   return code;
@@ -340,6 +342,132 @@ void putPath(const JValue &v, int len, uint64_t *&w, const char *what) {
   if ((int)sib.size() != len) throw ShapeErr(std::string(what) + ": Merkle path has " + std::to_string(sib.size()) + " siblings, shape expects " + std::to_string(len));
   for (auto &d : sib) putDigest(d, w);
 }
+
+// ---- fast path for p2v_parse_proof -----------------------------------------------------------------------------
+// serde_json writes `ProofWithPublicInputs` with the keys in declaration order and plain non-negative integers, so
+// the common case needs no tree at all: one forward scan that checks the expected punctuation and keys and converts
+// every number straight into its slot of the blob (eight digits at a time).  ANY deviation — other key order, a
+// negative / fractional / exponent token, a count that does not match the shape, malformed text — makes it return
+// false and the tape decoder below takes over (and produces the error, if there is one).  aeson accepts any key
+// order, so the slow path stays the definition; tests/test_host.py checks both against each other.
+struct FastScan {
+  const char *p, *end;
+  bool ok = true;
+  void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; }
+  bool ch(char c) {
+    ws();
+    if (p < end && *p == c) { p++; return true; }
+    return ok = false;
+  }
+  bool peek(char c) { ws(); return p < end && *p == c; }
+  bool key(const char *k) {  // "k":
+    ws();
+    size_t n = strlen(k);
+    if ((size_t)(end - p) < n + 3 || *p != '"' || memcmp(p + 1, k, n) != 0 || p[n + 1] != '"') return ok = false;
+    p += n + 2;
+    return ch(':');
+  }
+  bool felt(uint64_t &v) {
+    ws();
+    const char *t = p;
+    while (end - p >= 8 && eightDigits(p)) p += 8;
+    while (p < end && (unsigned)(*p - '0') < 10) p++;
+    size_t nd = (size_t)(p - t);
+    if (nd == 0 || nd > 38) return ok = false;
+    if (p < end && (*p == '.' || *p == 'e' || *p == 'E' || *p == '-' || *p == '+')) return ok = false;
+    const uint64_t P = 0xFFFFFFFF00000001ULL;
+    size_t n1 = nd > 19 ? nd - 19 : 0, i = 0;
+    uint64_t hi = 0, lo = 0;
+    for (; i < n1; i++) hi = hi * 10 + (unsigned)(t[i] - '0');
+    for (; i + 8 <= nd; i += 8) lo = lo * 100000000ULL + parseEightDigits(t + i);
+    for (; i < nd; i++) lo = lo * 10 + (unsigned)(t[i] - '0');
+    if (n1 == 0) v = lo >= P ? lo - P : lo;
+    else {
+      static const uint64_t TEN19 = 10000000000000000000ULL;
+      v = JValue::reduce128((unsigned __int128)hi * TEN19 + lo);
+    }
+    return true;
+  }
+  // [a, b, ...] of exactly `count` field elements
+  bool felts(int count, uint64_t *&w) {
+    if (!ch('[')) return false;
+    for (int i = 0; i < count; i++) {
+      if (i && !ch(',')) return false;
+      if (!felt(*w++)) return false;
+    }
+    return ch(']');
+  }
+  bool digest(uint64_t *&w) { return ch('{') && key("elements") && felts(4, w) && ch('}'); }
+  bool digests(int count, uint64_t *&w) {
+    if (!ch('[')) return false;
+    for (int i = 0; i < count; i++) {
+      if (i && !ch(',')) return false;
+      if (!digest(w)) return false;
+    }
+    return ch(']');
+  }
+  bool exts(int count, uint64_t *&w) {
+    if (!ch('[')) return false;
+    for (int i = 0; i < count; i++) {
+      if (i && !ch(',')) return false;
+      if (!felts(2, w)) return false;
+    }
+    return ch(']');
+  }
+  bool path(int len, uint64_t *&w) { return ch('{') && key("siblings") && digests(len, w) && ch('}'); }
+};
+
+static bool fastParseProof(const char *json, size_t len, const p2v_shape &s, const p2v_layout &L, uint64_t *out) {
+  FastScan f{json, json + len};
+  int ncap = 1 << s.cap_height;
+  uint64_t *w = out;
+  if (!(f.ch('{') && f.key("proof") && f.ch('{'))) return false;
+  if (!(f.key("wires_cap") && f.digests(ncap, w) && f.ch(','))) return false;
+  if (!(f.key("plonk_zs_partial_products_cap") && f.digests(ncap, w) && f.ch(','))) return false;
+  if (!(f.key("quotient_polys_cap") && f.digests(ncap, w) && f.ch(','))) return false;
+  if (!(f.key("openings") && f.ch('{'))) return false;
+  const char *names[9] = {"constants", "plonk_sigmas", "wires", "plonk_zs", "plonk_zs_next", "partial_products", "quotient_polys", "lookup_zs", "lookup_zs_next"};
+  const int counts[9] = {L.n_open_constants, L.n_open_sigmas, L.n_open_wires, L.n_open_zs, L.n_open_zs_next, L.n_open_pp, L.n_open_quotient, L.n_open_lookup_zs, L.n_open_lookup_zs_next};
+  for (int i = 0; i < 9; i++) {
+    if (i && !f.ch(',')) return false;
+    if (!(f.key(names[i]) && f.exts(counts[i], w))) return false;
+  }
+  if (!(f.ch('}') && f.ch(',') && f.key("opening_proof") && f.ch('{'))) return false;
+  if (!(f.key("commit_phase_merkle_caps") && f.ch('['))) return false;
+  for (int i = 0; i < s.num_steps; i++) {
+    if (i && !f.ch(',')) return false;
+    if (!f.digests(ncap, w)) return false;
+  }
+  if (!(f.ch(']') && f.ch(','))) return false;
+  if (w - out != L.off_final_poly) return false;
+  // query rounds come before final_poly / pow_witness / public_inputs in the text, after them in the blob
+  uint64_t *q = out + L.proof_words;
+  if (!(f.key("query_round_proofs") && f.ch('['))) return false;
+  for (int r = 0; r < s.num_queries; r++) {
+    if (r && !f.ch(',')) return false;
+    uint64_t *q0 = q;
+    if (!(f.ch('{') && f.key("initial_trees_proof") && f.ch('{') && f.key("evals_proofs") && f.ch('['))) return false;
+    for (int o = 0; o < 4; o++) {
+      if (o && !f.ch(',')) return false;
+      if (!(f.ch('[') && f.felts(L.oracle_width[o], q) && f.ch(',') && f.path(L.init_path_len, q) && f.ch(']'))) return false;
+    }
+    if (!(f.ch(']') && f.ch('}') && f.ch(',') && f.key("steps") && f.ch('['))) return false;
+    for (int st = 0; st < s.num_steps; st++) {
+      if (st && !f.ch(',')) return false;
+      if (!(f.ch('{') && f.key("evals") && f.exts(1 << s.step_arity_bits[st], q) && f.ch(',') && f.key("merkle_proof") &&
+            f.path(L.step_path_len[st], q) && f.ch('}')))
+        return false;
+    }
+    if (!(f.ch(']') && f.ch('}'))) return false;
+    if (q - q0 != L.query_words) return false;
+  }
+  if (!(f.ch(']') && f.ch(','))) return false;
+  if (!(f.key("final_poly") && f.ch('{') && f.key("coeffs") && f.exts(s.final_poly_len, w) && f.ch('}') && f.ch(','))) return false;
+  if (!(f.key("pow_witness") && f.felt(*w++) && f.ch('}') && f.ch('}') && f.ch(','))) return false;
+  if (!(f.key("public_inputs") && f.felts(s.num_public_inputs, w) && f.ch('}'))) return false;
+  f.ws();
+  return f.p == f.end && w - out == L.proof_words;
+}
 }  // namespace
 
 extern "C" {
@@ -548,6 +676,7 @@ int p2v_parse_proof(const char *json, size_t len, const p2v_shape *shape, uint64
   p2v_layout L;
   int rc = layoutImpl(*shape, L);
   if (rc) return rc;
+  if (!g_no_fast_parse && fastParseProof(json, len, *shape, L, out)) return P2V_OK;
   try {
     JsonDoc doc(json, len);
     JValue root = doc.root();

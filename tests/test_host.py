@@ -269,3 +269,21 @@ def test_batch_parse_on_threads(p2v):
         p2v.parse_proofs(texts, shape, threads=4)
     assert e.value.code == -5 and "proof 5" in str(e.value)
     assert p2v.parse_proofs([], shape).shape == (0, lay.blob_words)
+
+
+@pytest.mark.parametrize("name", ["small6", "lookup6", "real5", "s12"])
+def test_fast_scan_and_tape_decoders_agree(p2v, name):
+    """The forward-scan decoder (keys in serde's declaration order) and the tape decoder (any key order, like aeson)
+    give the same blob; re-ordered keys, indentation and exotic-but-legal number tokens fall back to the tape."""
+    shape, lay, vkey, blob = fixtures.load(name)
+    text = fixtures.read(name, "proof")
+    doc = json.loads(text)
+    assert np.array_equal(p2v.parse_proof(text, shape), blob)
+    assert np.array_equal(p2v.parse_proof(json.dumps(doc, sort_keys=True), shape), blob)      # other key order -> tape
+    assert np.array_equal(p2v.parse_proof(json.dumps(doc, indent=2), shape), blob)            # whitespace -> still fast
+    doc2 = json.loads(text)
+    pw = int(doc2["proof"]["opening_proof"]["pow_witness"])
+    big = json.dumps(doc2).replace('"pow_witness": %d' % pw, '"pow_witness": %d' % (pw + 5 * P * P * P))  # 58+ digits -> tape
+    assert np.array_equal(p2v.parse_proof(big, shape), blob)
+    texts = [text, json.dumps(doc, sort_keys=True), json.dumps(doc, indent=1)] * 3
+    assert np.array_equal(p2v.parse_proofs(texts, shape, threads=3), np.tile(blob, (9, 1)))
