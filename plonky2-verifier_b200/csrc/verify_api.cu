@@ -252,6 +252,7 @@ struct TracePoint { const char *what; int chunk; size_t m; cudaEvent_t ev; };
 #ifndef P2V_RAMP_START_DIV
 #define P2V_RAMP_START_DIV 8
 #endif
+
 int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t n, int what, Outputs out) {
   auto host_t0 = std::chrono::steady_clock::now();
   auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
@@ -317,17 +318,24 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   double host_setup = host_ms();
   mark("begin", -1, 0, ctx->stream);
   int k = 0;
-  // host input on the pipeline: ramp the first chunks up from chunk/8 so that the H2D copy that nothing can hide
-  // (the very first one) is short.  Growth is x9/8 per chunk: the copy of chunk k+1 must not take longer than
-  // the kernels of chunk k, and PCIe delivers proofs only ~1.3x faster than the GPU verifies them (55 GB/s =
-  // 4.3e5 S12 proofs/s against 3.3e5) — doubling left the GPU idle for ~25 ms per call waiting for copies.
-  // Measured at 10^5 S12 proofs from pinned memory (tools/ramp_sweep.sh): x2 292k, x1.5 296k, x1.25 300k,
-  // x1.125 319k, x1.0625 313k proofs/s; constant chunks of 2-8 k proofs 238k-308k.
-  // (Measured: ramping device-resident input only adds launches.)
-  size_t ramp = (!src_dev && depth >= 2 && chunk >= 8 * 1024) ? chunk / P2V_RAMP_START_DIV / 32 * 32 : chunk;
-  for (size_t c0 = 0, m = 0; c0 < n; c0 += m, k++) {
-    m = std::min(ramp, n - c0);
-    ramp = std::min(chunk, (ramp * P2V_RAMP_NUM / P2V_RAMP_DEN + 31) / 32 * 32);
+  // Chunk schedule: equal chunks, except for host input with a user-set chunk >= 8192 proofs, which ramps up from
+  // chunk/8 by x9/8 per chunk — the copy of chunk k+1 must not take longer than the kernels of chunk k, and PCIe
+  // delivers proofs only ~1.1x faster than the GPU verifies them (measured with 2 GiB chunks, tools/ramp_sweep.sh:
+  // x2 292k, x1.5 296k, x1.25 300k, x1.125 319k proofs/s).  (A taper of the default 0.5 GiB schedule at both ends —
+  // chunk/4, chunk/2, ..., chunk/2, chunk/4 — measured WORSE: 330k against 368k proofs/s.)
+  std::vector<size_t> sched;
+  {
+    bool ramped = !src_dev && depth >= 2 && chunk >= 8 * 1024;
+    size_t step = ramped ? chunk / P2V_RAMP_START_DIV / 32 * 32 : chunk;
+    for (size_t done = 0; done < n;) {
+      size_t m = std::min(step, n - done);
+      sched.push_back(m);
+      done += m;
+      if (ramped) step = std::min(chunk, (step * P2V_RAMP_NUM / P2V_RAMP_DEN + 31) / 32 * 32);
+    }
+  }
+  for (size_t c0 = 0; k < (int)sched.size(); c0 += sched[k], k++) {
+    const size_t m = sched[k];
     const u64 *src = blobs + c0 * blob_words;
     int b = k & 1;              // staging buffer (host input): two of them, released by K0
     int lane = k % depth;       // stream + workspace of this chunk
