@@ -355,7 +355,7 @@ def main():
                    "proofs_per_gpu": n, "blob_bytes": W * 8, "queries": shape.num_queries, "perms_per_proof": 114 + shape.num_queries * ppq,
                    "l2": "inputs (%.1f GB per step) are far larger than L2" % (n * W * 8 / 1e9),
                    "batch": "bundled %s fixture x %d, 3 of 4 copies tampered in one word" % (args.fixture, n),
-                   "verdict_histogram": hist, "host_numa": "process bound to the GPU's NUMA node (%d cpus) for the pinned staging buffers" % len(os.sched_getaffinity(0)), "pipeline": "3 lanes (stream + workspace); chunks of 2 GiB (device-resident input) / 0.5 GiB (host input); K0/K4/K5 of the next chunks overlap K6 of the current one", "multi_gpu": "contiguous slices + NCCL all_gather of the accept bitmap" if world > 1 else "single GPU"},
+                   "verdict_histogram": hist, "host_numa": "process bound to the GPU's NUMA node (%d cpus) for the pinned staging buffers" % len(os.sched_getaffinity(0)), "pipeline": "4 lanes (stream + workspace); chunks of 3 GiB (device-resident input) / 0.5 GiB (host input); K0/K4/K5 of the next chunks overlap K6 of the current one", "multi_gpu": "contiguous slices + NCCL all_gather of the accept bitmap" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * W * 8, "d2h_bytes_per_step": int(h_bits.nbytes + h_status.nbytes),
                 "proofs_per_gpu": n_e2e, "h2d_copy_gbs_measured": h2d_gbs,
                 "h2d_bound_proofs_per_s": h2d_gbs * 1e9 / (W * 8) * world},

@@ -275,7 +275,7 @@ int p2v_verify_groups(p2v_ctx *ctx, size_t n_groups, const p2v_circuit *const *c
                       const size_t *counts, uint32_t *const *accept_bits, uint32_t *const *status);
 /* Limit on proofs staged per pass (SoA workspace = chunk * blob_words * 8 bytes); 0 = default. */
 int p2v_ctx_set_chunk(p2v_ctx *ctx, size_t proofs_per_chunk);
-/* Chunk pipelining: depth 2..4 (default 3) runs consecutive chunks round-robin on that many streams and
+/* Chunk pipelining: depth 2..4 (default 4) runs consecutive chunks round-robin on that many streams and
  * workspaces, so the latency-bound per-proof kernels (K0, K4, K5) of the next chunk(s) overlap the Merkle kernel of
  * the current one; depth 1 is strictly serial and is the mode in which p2v_ctx_last_ms is meaningful.
  * Results are identical. */

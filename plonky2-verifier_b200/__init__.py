@@ -285,7 +285,7 @@ class pinned_u64:
 
 # ---- GPU context -------------------------------------------------------------------------------
 
-DEFAULT_PIPELINE = 3  # lanes of the chunk pipeline a new context starts with (p2v_ctx_set_pipeline)
+DEFAULT_PIPELINE = 4  # lanes of the chunk pipeline a new context starts with (p2v_ctx_set_pipeline)
 
 
 class Context:

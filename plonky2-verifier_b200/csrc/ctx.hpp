@@ -21,7 +21,7 @@ struct p2v_ctx {
   void *lane_ws[P2V_MAX_DEPTH] = {};             // [0] unused (= ws)
   size_t lane_ws_bytes[P2V_MAX_DEPTH] = {};
   cudaEvent_t lane_join[P2V_MAX_DEPTH] = {};
-  int pipeline = 3;                // 1 = strictly serial chunks (per-section timings valid), 2..P2V_MAX_DEPTH = overlapped
+  int pipeline = 4;                // 1 = strictly serial chunks (per-section timings valid), 2..P2V_MAX_DEPTH = overlapped
   cudaEvent_t fork_ev = nullptr;
   std::string err;
   uint64_t launches = 0;

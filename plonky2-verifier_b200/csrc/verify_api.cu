@@ -265,13 +265,13 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   bool src_dev = p2v_is_device_ptr(blobs);
   // Chunking.  Serial mode: as few chunks as memory allows.  Pipelined mode (default): chunks go round-robin over
   // `pipeline` lanes (stream + workspace each), so K0+K4+K5 of the next chunks (latency-bound, one thread per proof)
-  // fill the GPU next to the Merkle kernel of the current one.  Device-resident input: ~2 GiB chunks.  Host input:
+  // fill the GPU next to the Merkle kernel of the current one.  Device-resident input: ~3 GiB chunks.  Host input:
   // ~0.5 GiB chunks — a chunk cannot start before it has arrived, PCIe delivers proofs only ~1.1x faster than the
   // GPU verifies them, so there is never a backlog of big chunks to overlap; small constant chunks on 3 lanes
   // measured 370 k proofs/s end to end against 348 k for 2 GiB chunks behind a ramp (tools/chunk_sweep.sh).
   size_t chunk = ctx->chunk;
   if (chunk == 0) {
-    size_t budget = ctx->pipeline > 1 ? (src_dev ? ((size_t)2 << 30) : ((size_t)512 << 20)) : (src_dev ? ((size_t)16 << 30) : ((size_t)2 << 30));
+    size_t budget = ctx->pipeline > 1 ? (src_dev ? ((size_t)3 << 30) : ((size_t)512 << 20)) : (src_dev ? ((size_t)16 << 30) : ((size_t)2 << 30));
     chunk = budget / (blob_words * 8);
     if (chunk < 1024) chunk = 1024;
   }

@@ -88,8 +88,8 @@ def test_chunked_and_device_resident(p2v, ctx, orc):
     blobs, words, deltas = fixtures.tampered_batch(blob, lay, shape, n, seed=3)
     acc0, st0 = cir.verifyProof(blobs)
     ctx.set_chunk(64)
-    acc1, st1 = cir.verifyProof(blobs)       # 4 chunks on the multi-lane pipeline (default depth 3)
-    for depth in (1, 2, 4):                  # strictly serial, two lanes, four lanes
+    acc1, st1 = cir.verifyProof(blobs)       # 4 chunks on the multi-lane pipeline (default depth 4)
+    for depth in (1, 2, 3):                  # strictly serial, two lanes, three lanes
         ctx.set_pipeline(depth)
         acc3, st3 = cir.verifyProof(blobs)
         assert np.array_equal(st1, st3) and np.array_equal(acc1, acc3), depth

@@ -9,8 +9,10 @@ ctx = p2v.Context(0); cir = p2v.Circuit(ctx, shape, vkey)
 W = lay.blob_words
 d = torch.from_numpy(np.tile(blob, (n, 1)).view(np.int64)).cuda(); torch.cuda.synchronize()
 dbits = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda"); dst = torch.zeros(n, dtype=torch.int32, device="cuda")
-for chunk in (1024, 2048, 3072, 4096, 6144, 8192, 16896):
-    for depth in (1, 2, 3):
+chunks = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1024, 2048, 3072, 4096, 6144, 8192, 16896]
+depths = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1, 2, 3]
+for chunk in chunks:
+    for depth in depths:
         ctx.set_chunk(chunk); ctx.set_pipeline(depth)
         ts = []
         for i in range(4):
