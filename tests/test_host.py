@@ -287,3 +287,21 @@ def test_fast_scan_and_tape_decoders_agree(p2v, name):
     assert np.array_equal(p2v.parse_proof(big, shape), blob)
     texts = [text, json.dumps(doc, sort_keys=True), json.dumps(doc, indent=1)] * 3
     assert np.array_equal(p2v.parse_proofs(texts, shape, threads=3), np.tile(blob, (9, 1)))
+
+
+def test_differential_fuzz_of_the_two_proof_decoders(p2v):
+    """1500 randomly mutated proof texts (byte flips, deletions, insertions, truncations): the forward-scan fast path
+    + tape fallback and the tape decoder alone must agree on every outcome — same blob or same error code — and
+    neither may crash."""
+    import subprocess
+    import sys
+
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz_parse.py")
+    outs = []
+    for extra in ({}, {"P2V_NO_FAST_PARSE": "1"}):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, script, "1500"], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.split())
+    assert outs[0] == outs[1]
+    assert int(outs[0][1]) > 50 and int(outs[0][2]) > 500  # both accepted and rejected mutants occurred
