@@ -256,6 +256,7 @@ inline JList JValue::list() const {
 class JsonDoc {
  public:
   JsonDoc(const char *p, size_t n) : p_(p), end_(p + n) {
+    if (n > 0x7fffffffu) throw JsonError("document larger than 2 GiB");  // node indices and token lengths are 32-bit
     tape_.reserve(n / 12 + 16);
     value(0);
     ws();
