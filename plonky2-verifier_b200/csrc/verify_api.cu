@@ -372,11 +372,15 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     // K6
     if (what & RUN_FRI) {
       size_t items = m * (size_t)d.Q * (4 + d.nsteps);
-      // serial mode: persistent grid; pipelined mode: one block per P2V_MERKLE_BLOCK openings, so that blocks of
-      // all lanes' kernels interleave on the SMs as resources free up
-      unsigned grid = depth >= 2 ? (unsigned)((items + P2V_MERKLE_BLOCK - 1) / P2V_MERKLE_BLOCK)
-                                 : (unsigned)p2v_grid_for(ctx, items, P2V_MERKLE_BLOCK, P2V_MERKLE_MINBLOCKS);
-      P2V_LAUNCH_ON(ctx, st, k_fri_merkle, grid, P2V_MERKLE_BLOCK, 0, d, ws, m);
+      // serial mode: persistent grid of 256-thread blocks; pipelined mode: one 128-thread block per 128 openings, so
+      // that blocks of all lanes' kernels interleave on the SMs as resources free up
+      if (depth >= 2) {
+        unsigned grid = (unsigned)((items + P2V_MERKLE_BLOCK_PIPE - 1) / P2V_MERKLE_BLOCK_PIPE);
+        P2V_LAUNCH_ON(ctx, st, (k_fri_merkle<P2V_MERKLE_BLOCK_PIPE, P2V_MERKLE_MINBLOCKS_PIPE>), grid, P2V_MERKLE_BLOCK_PIPE, 0, d, ws, m);
+      } else {
+        unsigned grid = (unsigned)p2v_grid_for(ctx, items, P2V_MERKLE_BLOCK, P2V_MERKLE_MINBLOCKS);
+        P2V_LAUNCH_ON(ctx, st, (k_fri_merkle<P2V_MERKLE_BLOCK, P2V_MERKLE_MINBLOCKS>), grid, P2V_MERKLE_BLOCK, 0, d, ws, m);
+      }
       if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
       P2V_LAUNCH_ON(ctx, st, k_fri_query, p2v_grid_for(ctx, m * d.Q, 256, 4), 256, 0, d, ws, m);
     }
