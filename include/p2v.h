@@ -273,7 +273,8 @@ int p2v_verify_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, 
  * (the circuit is a kernel parameter).  Stops at the first group that fails with an error code. */
 int p2v_verify_groups(p2v_ctx *ctx, size_t n_groups, const p2v_circuit *const *circuits, const uint64_t *const *blobs,
                       const size_t *counts, uint32_t *const *accept_bits, uint32_t *const *status);
-/* Limit on proofs staged per pass (SoA workspace = chunk * blob_words * 8 bytes); 0 = default. */
+/* Proofs per chunk (SoA workspace per pipeline lane ~ 1.1 * chunk * blob_words * 8 bytes).  0 = default: 3 GiB of
+ * blobs for device-resident input, 0.5 GiB for host input (16 GiB / 2 GiB with p2v_ctx_set_pipeline(ctx, 1)). */
 int p2v_ctx_set_chunk(p2v_ctx *ctx, size_t proofs_per_chunk);
 /* Chunk pipelining: depth 2..4 (default 4) runs consecutive chunks round-robin on that many streams and
  * workspaces, so the latency-bound per-proof kernels (K0, K4, K5) of the next chunk(s) overlap the Merkle kernel of
