@@ -266,6 +266,28 @@ int p2v_fri(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n,
  *   accept_bits: ceil(n/32) words; status: [n] (may be NULL). */
 int p2v_verify_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n,
                      uint32_t *accept_bits, uint32_t *status);
+/* `verifyProof` with every intermediate the north star names — challenges, combined constraint values, quotient-identity
+ * verdicts, per-query status, folded evaluations, RECOMPUTED MERKLE ROOTS — in one call; every pointer is optional.
+ *   challenges_in  test hook: SoA [p2v_challenges_words][n] challenges that REPLACE the Fiat-Shamir transcript's, so that
+ *                  branches no honest transcript reaches can be compared with the oracle (zeta = 1 in `evalLagrange0`,
+ *                  Algebra/Poly.hs:14-17; x = zeta in `combineInitial`, Plonk/FRI.hs:151-207 with `inv 0 = 0`,
+ *                  Algebra/Goldilocks.hs:155); query indices are taken mod 2^lde_bits;
+ *   roots          SoA [(4+num_steps)*4][n*num_queries]: word i of the root `reconstructMerkleRoot'` (Hash/Merkle.hs:30-37)
+ *                  yields for tree t (0..3 the initial oracles, 4.. the folding steps) of (proof p, query q) at
+ *                  plane t*4+i, index p*num_queries+q — computed whatever the verdict is. */
+typedef struct p2v_intermediates {
+  const uint64_t *challenges_in;
+  uint64_t *challenges;   /* SoA [p2v_challenges_words][n]                    */
+  uint64_t *combined;     /* SoA [2*num_challenges][n]                        */
+  uint8_t *eq_ok_mask;    /* [n]                                              */
+  uint32_t *status;       /* [n] verifyProof verdict                          */
+  uint32_t *accept_bits;  /* ceil(n/32) words                                 */
+  uint32_t *query_status; /* [n][num_queries]                                 */
+  uint64_t *folded;       /* SoA [2][n*num_queries]                           */
+  uint64_t *roots;        /* SoA [(4+num_steps)*4][n*num_queries]             */
+} p2v_intermediates;
+int p2v_verify_intermediates(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n, const p2v_intermediates *io);
+
 /* Heterogeneous batches: proofs of DIFFERENT circuits (other degree_bits, gate sets, FRI parameters,
  * lookups ...) grouped by circuit; group g is verified exactly like p2v_verify_batch(ctx, circuits[g], blobs[g],
  * counts[g], accept_bits[g], status[g]) — `map (uncurry verifyProof)` over (vkey, proof) pairs that do not share a
@@ -273,6 +295,39 @@ int p2v_verify_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, 
  * (the circuit is a kernel parameter).  Stops at the first group that fails with an error code. */
 int p2v_verify_groups(p2v_ctx *ctx, size_t n_groups, const p2v_circuit *const *circuits, const uint64_t *const *blobs,
                       const size_t *counts, uint32_t *const *accept_bits, uint32_t *const *status);
+/* ---- multi-GPU: one process per GPU, contiguous slices, ONE all-gather of the accept bitmap ------ */
+/* The slicing rule.  slice_len = ceil(n_total / world) rounded up to a multiple of 32 (bitmap words never straddle two
+ * ranks); rank r owns proofs [min(n_total, r*slice_len), min(n_total, (r+1)*slice_len)) — the last ranks may be short
+ * or empty. */
+size_t p2v_shard_slice_len(size_t n_total, int world);
+int p2v_shard_bounds(size_t n_total, int rank, int world, size_t *start, size_t *stop);
+/* Communicator bootstrap for hosts that have none (NCCL, bound at run time: libnccl.so.2).  Rank 0 calls
+ * p2v_nccl_unique_id (128 bytes), ships the id to the other ranks by any means (a file, a socket, MPI, torch's store),
+ * then every rank calls p2v_nccl_init (collective).  The communicator belongs to the context and dies with it. */
+#define P2V_NCCL_UNIQUE_ID_BYTES 128
+int p2v_nccl_unique_id(void *out128);
+int p2v_nccl_init(p2v_ctx *ctx, const void *id128, int rank, int world);
+/* ... or use an ncclComm_t the caller owns (rank and world are read from it; it is not destroyed by the library). */
+int p2v_nccl_attach(p2v_ctx *ctx, void *nccl_comm);
+int p2v_nccl_finalize(p2v_ctx *ctx);
+/* rank / world of the attached communicator (0 / 1 without one) and the NCCL version in use (0: library not found) */
+int p2v_nccl_info(p2v_ctx *ctx, int *rank, int *world, int *nccl_version);
+/* `verifyProof` (Plonk/Verifier.hs:56-65) mapped over a batch of n_total proofs that is sharded over `world` GPUs:
+ * this rank verifies its slice (blobs_local: AoS [stop-start][blob_words], host or device) and the packed accept bits
+ * are all-gathered with ncclAllGather on the context's stream (in place, no host synchronisation in between).
+ *   accept_bits_full: world * slice_len / 32 words, host or device; on return its first ceil(n_total/32) words are the
+ *                     accept bitmap of the WHOLE batch — identical on every rank and identical to what one GPU
+ *                     computes for the whole batch; padding bits are 0;
+ *   status_local:     [stop-start] status words of this rank's proofs (may be NULL).
+ * Collective: every rank of the communicator calls it with the same n_total.  world == 1 needs no communicator. */
+int p2v_verify_batch_sharded(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs_local, size_t n_total, int rank,
+                             int world, uint32_t *accept_bits_full, uint32_t *status_local);
+
+/* K0 alone: AoS blobs [n][blob_words] -> structure-of-arrays word planes, the layout every kernel reads
+ * (replaces the Haskell lists of Types.hs:251-279).  planes_out (device or host): [blob_words][n] with plane order
+ * pp[w] for w < proof_words, then qp[wq * num_queries + q] for wq < query_words. */
+int p2v_stage(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n, uint64_t *planes_out);
+
 /* Proofs per chunk (SoA workspace per pipeline lane ~ 1.1 * chunk * blob_words * 8 bytes).  0 = default: 3 GiB of
  * blobs for device-resident input, 0.5 GiB for host input (16 GiB / 2 GiB with p2v_ctx_set_pipeline(ctx, 1)). */
 int p2v_ctx_set_chunk(p2v_ctx *ctx, size_t proofs_per_chunk);
@@ -288,11 +343,20 @@ int p2v_ctx_set_pipeline(p2v_ctx *ctx, int depth);
 int p2v_synth_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *template_blob, size_t n,
                     const int32_t *tamper_word, const uint64_t *tamper_delta, uint64_t *blobs_out);
 
+/* ---- test hooks ------------------------------------------------------------------ */
+/* The device field routines one by one (Algebra/Goldilocks.hs:140-175, GoldilocksExt.hs:54-99) on caller-chosen operands;
+ * inputs may be any u64 (lazy representation), outputs are canonical.  Base field, arrays [n]:
+ *   0 a+b, 1 a-b, 2 a*b, 3 inv a (inv 0 = 0), 4 -a, 5 a * (u32)b, 6 (b:a) mod p as a 128-bit value, 7 a^b, 8 canonical a,
+ *   9 a^7 (s-box).  Extension field, arrays SoA [2][n]: 16 a*b, 17 inv a, 18 a+b, 19 a-b, 20 a^2, 21 b.re * a, 22 a*X,
+ *   23 a^(b.re), 24 -a.  b may be NULL for unary operations. */
+int p2v_debug_field_op(p2v_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+
 /* ---- measurement helpers ------------------------------------------------------- */
 /* Integer-pipe peak microbenchmark: dependent chains whose every step is a GROUP of instructions:
  * mode 0: LOP3 + IMAD.WIDE.U32, 1: 2 LOP3 + IMAD.WIDE.U32, 2: LOP3 + IMAD (32-bit), 3: LOP3 + IADD3,
  * 4: 2 IMAD.WIDE.U32 + LOP3, 5: 2 IMAD (32-bit), 6: 2 LOP3, 7: IMAD.WIDE.U32 alone, 8: 2 SHF, 9: IADD3 + IADD3.X,
- * 10: DFMA, 11: DFMA + LOP3 + IMAD, 12: DADD.
+ * 10: DFMA, 11: DFMA + LOP3 + IMAD, 12: DADD, 13: I2F.F64.U32 + LOP3, 14: mode 13 next to a DFMA chain,
+ * 15: mode 13 next to an IMAD.WIDE.U32 chain.
  * *ops_per_s = groups per second summed over all threads. */
 int p2v_int_pipe_peak(p2v_ctx *ctx, int mode, double *ops_per_s);
 /* Device time (ms) of a section of the most recent batch call (last chunk): "stage" (K0), "challenges" (K4),

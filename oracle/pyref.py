@@ -468,6 +468,7 @@ def verify(common, vkey, proof, trace=None):
         combined.append(acc)
     if trace is not None:
         trace["combined"] = [x for c in combined for x in c.pair()]
+        trace["pih"] = list(pih)
     # ---- checkCombinedPlonkEquations', Plonk/Verifier.hs:35-52
     mask = 0
     q = op["quotient_polys"]
@@ -550,3 +551,30 @@ def eprod(xs):
 def load_fixture(golden_dir, name, common_name=None):
     rd = lambda n, k: json.load(open(os.path.join(golden_dir, "%s_%s.json" % (n, k))))
     return rd(common_name or name, "common"), rd(name, "vkey"), rd(name, "proof")
+
+
+def testmain_text(common, vkey, proof):
+    """Exactly what the reference's driver prints for this proof (src/testmain.hs:40-63) with the reference's Show
+    instances: `MkDigest a b c d` (derived Show, Hash/Digest.hs:36-38, over Goldilocks' decimal `show`,
+    Algebra/Goldilocks.hs:90-91), `(re + X*im)` (Algebra/GoldilocksExt.hs:37-38), Haskell list / Bool syntax.  A proof that
+    hits one of the reference's `error` sites ends with `testmain: <message>` (what GHC prints on stderr before aborting);
+    the messages are the ones at Plonk/FRI.hs:108, :310, :311."""
+    tr = {}
+    st = verify(common, vkey, proof, tr)
+    op = proof["proof"]["openings"]
+    out = ["public inputs hash = MkDigest %d %d %d %d" % tuple(tr["pih"][:4])]
+    for k in ("constants", "plonk_sigmas", "wires", "plonk_zs", "plonk_zs_next", "partial_products", "quotient_polys", "lookup_zs", "lookup_zs_next"):
+        out.append("%-26s = %d" % ("# opening_" + k, len(op[k])))
+    comb = tr["combined"]
+    out.append("[" + ",".join("(%d + X*%d)" % (comb[2 * i], comb[2 * i + 1]) for i in range(len(comb) // 2)) + "]")
+    r = common["config"]["num_challenges"]
+    mask = (st >> 16) if (st & 0xFF) == 1 else 0
+    out.append("[" + ",".join("False" if (mask >> i) & 1 else "True" for i in range(r)) + "]")
+    code = st & 0xFF
+    verdict = {0: "True", 1: "False", 2: "False", 3: "False",
+               16: "testmain: checkInitialTreeProofs: at least one Merkle proof failed",
+               17: "testmain: folding step Merkle proof does not check out",
+               18: "testmain: folding step evaluation does not match the opening"}.get(code, "testmain: error site %d" % code)
+    out.append("proof verification result = " + verdict)
+    return "\n".join(out) + "\n"
+

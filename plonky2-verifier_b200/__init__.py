@@ -19,7 +19,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libp2v.so")
+# P2V_LIB_PATH: tuning aid only (tools/variants_prebuilt.sh loads compile-time variants of the same library)
+LIB_PATH = os.environ.get("P2V_LIB_PATH") or os.path.join(_HERE, "libp2v.so")
 
 P2V_MAX_GATES = 32
 P2V_MAX_GROUPS = 8
@@ -84,6 +85,11 @@ class Layout(C.Structure):
     ]
 
 
+class Intermediates(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("challenges_in", "challenges", "combined", "eq_ok_mask", "status", "accept_bits",
+                                           "query_status", "folded", "roots")]
+
+
 _lib = None
 
 
@@ -141,6 +147,17 @@ def lib():
         "p2v_ctx_set_chunk": (C.c_int, [vp, sz]),
         "p2v_ctx_set_pipeline": (C.c_int, [vp, C.c_int]),
         "p2v_synth_batch": (C.c_int, [vp, vp, u64p, sz, C.c_void_p, u64p, u64p]),
+        "p2v_shard_slice_len": (sz, [sz, C.c_int]),
+        "p2v_shard_bounds": (C.c_int, [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]),
+        "p2v_nccl_unique_id": (C.c_int, [vp]),
+        "p2v_nccl_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "p2v_nccl_attach": (C.c_int, [vp, vp]),
+        "p2v_nccl_finalize": (C.c_int, [vp]),
+        "p2v_nccl_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "p2v_verify_batch_sharded": (C.c_int, [vp, vp, u64p, sz, C.c_int, C.c_int, u32p, u32p]),
+        "p2v_stage": (C.c_int, [vp, vp, u64p, sz, u64p]),
+        "p2v_verify_intermediates": (C.c_int, [vp, vp, u64p, sz, C.POINTER(Intermediates)]),
+        "p2v_debug_field_op": (C.c_int, [vp, C.c_int, u64p, u64p, u64p, sz]),
         "p2v_int_pipe_peak": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double)]),
         "p2v_ctx_last_ms": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_float)]),
     }
@@ -159,6 +176,8 @@ EXPORTED_SYMBOLS = [
     "p2v_shape_free", "p2v_parse_gate", "p2v_shape_layout", "p2v_challenges_words", "p2v_parse_vkey",
     "p2v_parse_proof", "p2v_parse_proofs", "p2v_circuit_create", "p2v_circuit_destroy", "p2v_challenges", "p2v_constraints",
     "p2v_fri", "p2v_verify_batch", "p2v_verify_groups", "p2v_ctx_set_chunk", "p2v_ctx_set_pipeline", "p2v_synth_batch", "p2v_int_pipe_peak", "p2v_ctx_last_ms",
+    "p2v_shard_slice_len", "p2v_shard_bounds", "p2v_nccl_unique_id", "p2v_nccl_init", "p2v_nccl_attach", "p2v_nccl_finalize",
+    "p2v_nccl_info", "p2v_verify_batch_sharded", "p2v_stage", "p2v_verify_intermediates", "p2v_debug_field_op",
 ]
 
 
@@ -330,6 +349,20 @@ class Context:
     def set_pipeline(self, depth):
         self._check(lib().p2v_ctx_set_pipeline(self._h, int(depth)))
 
+    # -- multi-GPU (sharded_api.cu) --
+    def nccl_init(self, unique_id, rank, world):
+        """Collective: join the communicator named by `unique_id` (128 bytes from `nccl_unique_id()` on rank 0)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(lib().p2v_nccl_init(self._h, C.cast(buf, C.c_void_p), int(rank), int(world)))
+
+    def nccl_info(self):
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        self._check(lib().p2v_nccl_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
+        return r.value, w.value, v.value
+
+    def nccl_finalize(self):
+        self._check(lib().p2v_nccl_finalize(self._h))
+
     def last_ms(self, section):
         v = C.c_float()
         self._check(lib().p2v_ctx_last_ms(self._h, section.encode(), C.byref(v)))
@@ -339,6 +372,15 @@ class Context:
         v = C.c_double()
         self._check(lib().p2v_int_pipe_peak(self._h, int(mode), C.byref(v)))
         return v.value
+
+    def field_op(self, op, a, b=None):
+        """Test hook p2v_debug_field_op: one device field routine on arrays of operands (see include/p2v.h)."""
+        a = _u64(a)
+        b = None if b is None else _u64(b)
+        out = np.empty_like(a)
+        n = a.shape[-1]
+        self._check(lib().p2v_debug_field_op(self._h, int(op), _ptr(a), _ptr(b), _ptr(out), n))
+        return out
 
     # -- L2 Hash (names follow src/Hash/*.hs) --
     def permutation(self, states, out=None):
@@ -399,6 +441,27 @@ class Context:
         self._check(lib().p2v_merkle_open(self._h, _ptr(leaves), w, log_n, cap_height, _ptr(digests), _ptr(idx), n,
                                           _ptr(leaves_out), _ptr(sibs_out), _ptr(cap_out)))
         return leaves_out, sibs_out, cap_out
+
+
+def nccl_unique_id():
+    """128 opaque bytes naming a new communicator (rank 0 creates it and ships it to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().p2v_nccl_unique_id(C.cast(buf, C.c_void_p))
+    if rc:
+        raise P2VError(rc, lib().p2v_last_error(None).decode())
+    return buf.raw
+
+
+def shard_slice_len(n_total, world):
+    return int(lib().p2v_shard_slice_len(int(n_total), int(world)))
+
+
+def shard_bounds(n_total, rank, world):
+    a, b = C.c_size_t(), C.c_size_t()
+    rc = lib().p2v_shard_bounds(int(n_total), int(rank), int(world), C.byref(a), C.byref(b))
+    if rc:
+        raise P2VError(rc, "p2v_shard_bounds: bad rank/world")
+    return a.value, b.value
 
 
 def verify_groups(ctx, groups):
@@ -488,6 +551,57 @@ class Circuit:
             status = np.empty(n, dtype=np.uint32)
         self.ctx._check(lib().p2v_verify_batch(self.ctx._h, self._h, _ptr(blobs), n, _ptr(accept_bits), _ptr(status)))
         return (unpack_bits(accept_bits, n), status) if host else (accept_bits, status)
+
+    def verifyIntermediates(self, blobs, n=None, challenges_in=None, want_roots=True):
+        """`verifyProof` with every intermediate (p2v_verify_intermediates) -> dict of host arrays: challenges [cw][n],
+        combined [2r][n], eqmask [n], status [n], accept bool[n], qstatus [n][Q], folded [2][n*Q], roots [(4+steps)*4][n*Q].
+        challenges_in (SoA [cw][n]) replaces the transcript's challenges (test hook)."""
+        n = self._n(blobs, n)
+        sh = self.shape
+        cw, Q, r = challenges_words(sh), sh.num_queries, sh.num_challenges
+        out = dict(challenges=np.empty((cw, n), dtype=np.uint64), combined=np.empty((2 * r, n), dtype=np.uint64),
+                   eqmask=np.empty(n, dtype=np.uint8), status=np.empty(n, dtype=np.uint32),
+                   qstatus=np.empty((n, Q), dtype=np.uint32), folded=np.empty((2, n * Q), dtype=np.uint64))
+        bits = np.zeros((n + 31) // 32, dtype=np.uint32)
+        if want_roots:
+            out["roots"] = np.empty(((4 + sh.num_steps) * 4, n * Q), dtype=np.uint64)
+        io = Intermediates()
+        cin = None
+        if challenges_in is not None:
+            cin = _u64(challenges_in)
+            assert cin.shape == (cw, n)
+            io.challenges_in = _ptr(cin)
+        io.challenges, io.combined, io.eq_ok_mask = _ptr(out["challenges"]), _ptr(out["combined"]), _ptr(out["eqmask"])
+        io.status, io.accept_bits, io.query_status, io.folded = _ptr(out["status"]), _ptr(bits), _ptr(out["qstatus"]), _ptr(out["folded"])
+        io.roots = _ptr(out.get("roots"))
+        self.ctx._check(lib().p2v_verify_intermediates(self.ctx._h, self._h, _ptr(blobs), n, C.byref(io)))
+        out["accept"] = unpack_bits(bits, n)
+        return out
+
+    def verifyProofSharded(self, blobs_local, n_total, rank, world, accept_bits_full=None, status=None):
+        """`verifyProof` over a batch sharded across `world` GPUs (p2v_verify_batch_sharded): verifies this rank's slice and
+        all-gathers the accept bitmap -> (bitmap of the WHOLE batch, status of the local slice).  With the default host
+        outputs the call is synchronous and returns (accept bool[n_total], status u32[n_local]); with caller-supplied
+        device tensors it is asynchronous on the context's stream."""
+        start, stop = shard_bounds(n_total, rank, world)
+        n_local = stop - start
+        words_full = shard_slice_len(n_total, world) // 32 * world
+        host = accept_bits_full is None
+        if accept_bits_full is None:
+            accept_bits_full = np.zeros(max(words_full, 1), dtype=np.uint32)
+        if status is None:
+            status = np.empty(max(n_local, 1), dtype=np.uint32)
+        self.ctx._check(lib().p2v_verify_batch_sharded(self.ctx._h, self._h, _ptr(blobs_local) if n_local else None, int(n_total), int(rank),
+                                                       int(world), _ptr(accept_bits_full), _ptr(status)))
+        return (unpack_bits(accept_bits_full, n_total), status[:n_local]) if host else (accept_bits_full, status)
+
+    def stage(self, blobs, n=None, out=None):
+        """K0 alone (p2v_stage): AoS blobs -> word planes [blob_words][n]."""
+        n = self._n(blobs, n)
+        if out is None:
+            out = np.empty((self.layout.blob_words, n), dtype=np.uint64)
+        self.ctx._check(lib().p2v_stage(self.ctx._h, self._h, _ptr(blobs), n, _ptr(out)))
+        return out
 
     def verifyProofJson(self, json_texts, threads=0):
         """What `testmain` does for one proof (src/testmain.hs:31-63), for a batch: decode the `*_proof.json` texts on

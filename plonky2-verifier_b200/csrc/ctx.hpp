@@ -39,6 +39,10 @@ struct p2v_ctx {
   // back to the driver and the next call re-maps them, which cost 30-160 ms of host time per call at random
   // (measured with P2V_TRACE: identical GPU timelines, end-to-end throughput between 2.0e5 and 3.4e5 proofs/s).
   cudaMemPool_t pool = nullptr;
+  // multi-GPU (sharded_api.cu): communicator for the accept-bitmap all-gather
+  void *nccl_comm = nullptr;   // ncclComm_t
+  bool nccl_owned = false;     // created by p2v_nccl_init (destroyed with the context) or attached by the caller
+  int nccl_rank = 0, nccl_world = 1;
 };
 
 extern thread_local std::string p2v_tls_error;

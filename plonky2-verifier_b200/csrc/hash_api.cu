@@ -4,6 +4,31 @@
 
 thread_local std::string p2v_tls_error;
 
+// streams, events and the private pool of a new context; on failure the caller destroys the partly built context
+static int ctxInit(p2v_ctx *ctx, int device) {
+  P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 1; i < P2V_MAX_DEPTH; i++) {
+    P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->lane_stream[i], cudaStreamNonBlocking));
+    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->lane_join[i], cudaEventDisableTiming));
+  }
+  P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+  for (auto &ev : ctx->ev) P2V_CUDA(nullptr, cudaEventCreate(&ev));
+  for (int i = 0; i < 2; i++) {
+    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming));
+    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->compute_done[i], cudaEventDisableTiming));
+  }
+  cudaMemPoolProps props = {};
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = device;
+  P2V_CUDA(nullptr, cudaMemPoolCreate(&ctx->pool, &props));
+  uint64_t keep = UINT64_MAX;
+  P2V_CUDA(nullptr, cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  return P2V_OK;
+}
+
 extern "C" {
 
 int p2v_abi_version(void) { return P2V_ABI_VERSION; }
@@ -28,27 +53,11 @@ int p2v_ctx_create(int device, p2v_ctx **out) {
   p2v_ctx *ctx = new p2v_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  for (int i = 1; i < P2V_MAX_DEPTH; i++) {
-    P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->lane_stream[i], cudaStreamNonBlocking));
-    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->lane_join[i], cudaEventDisableTiming));
-  }
-  P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
-  for (auto &ev : ctx->ev) P2V_CUDA(nullptr, cudaEventCreate(&ev));
-  for (int i = 0; i < 2; i++) {
-    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming));
-    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->compute_done[i], cudaEventDisableTiming));
-  }
-  {
-    cudaMemPoolProps props = {};
-    props.allocType = cudaMemAllocationTypePinned;
-    props.handleTypes = cudaMemHandleTypeNone;
-    props.location.type = cudaMemLocationTypeDevice;
-    props.location.id = device;
-    P2V_CUDA(nullptr, cudaMemPoolCreate(&ctx->pool, &props));
-    uint64_t keep = UINT64_MAX;
-    P2V_CUDA(nullptr, cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  int rc = ctxInit(ctx, device);
+  if (rc != P2V_OK) {
+    std::string why = p2v_tls_error;  // p2v_ctx_destroy tolerates a partly built context
+    p2v_ctx_destroy(ctx);
+    return p2v_fail(nullptr, rc, why);
   }
   *out = ctx;
   return P2V_OK;
@@ -57,14 +66,16 @@ int p2v_ctx_create(int device, p2v_ctx **out) {
 void p2v_ctx_destroy(p2v_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  cudaStreamSynchronize(ctx->copy_stream);
-  for (int i = 1; i < P2V_MAX_DEPTH; i++) cudaStreamSynchronize(ctx->lane_stream[i]);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  for (int i = 1; i < P2V_MAX_DEPTH; i++)
+    if (ctx->lane_stream[i]) cudaStreamSynchronize(ctx->lane_stream[i]);
+  p2v_nccl_finalize(ctx);
   if (ctx->ws) cudaFree(ctx->ws);
   for (int i = 1; i < P2V_MAX_DEPTH; i++) {
     if (ctx->lane_ws[i]) cudaFree(ctx->lane_ws[i]);
     if (ctx->lane_join[i]) cudaEventDestroy(ctx->lane_join[i]);
-    cudaStreamDestroy(ctx->lane_stream[i]);
+    if (ctx->lane_stream[i]) cudaStreamDestroy(ctx->lane_stream[i]);
   }
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
@@ -76,8 +87,9 @@ void p2v_ctx_destroy(p2v_ctx *ctx) {
     if (ctx->copy_done[i]) cudaEventDestroy(ctx->copy_done[i]);
     if (ctx->compute_done[i]) cudaEventDestroy(ctx->compute_done[i]);
   }
-  cudaStreamDestroy(ctx->stream);
-  cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  cudaGetLastError();
   delete ctx;
 }
 
@@ -126,7 +138,11 @@ int p2v_poseidon_permute(p2v_ctx *ctx, const uint64_t *in, uint64_t *out, size_t
   int rc;
   if ((rc = din.init(ctx, in, n * 12 * sizeof(u64)))) return rc;
   if ((rc = dout.init(ctx, out, n * 12 * sizeof(u64)))) return rc;
+#if P2V_DUAL
+  P2V_LAUNCH(ctx, k_poseidon_permute2, p2v_grid_for(ctx, (n + 1) / 2, 128, 32), 128, 0, din.as<u64>(), dout.as<u64>(), n);
+#else
   P2V_LAUNCH(ctx, k_poseidon_permute, p2v_grid_for(ctx, n, 256, 16), 256, 0, din.as<u64>(), dout.as<u64>(), n);
+#endif
   if ((rc = dout.finish())) return rc;
   if (dout.host) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return P2V_OK;
@@ -251,9 +267,27 @@ int p2v_merkle_open(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, uint32_t l
   return P2V_OK;
 }
 
+// ---- test hook: device field arithmetic --------------------------------------------------------
+int p2v_debug_field_op(p2v_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
+  if (!ctx || !a || !out || op < 0 || op > 24) return p2v_fail(ctx, P2V_E_INVALID, "p2v_debug_field_op: bad argument");
+  if (n == 0) return P2V_OK;
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t words = op < 16 ? n : 2 * n;
+  DevIn da, db;
+  DevOut dout;
+  int rc;
+  if ((rc = da.init(ctx, a, words * 8))) return rc;
+  if ((rc = db.init(ctx, b, words * 8))) return rc;
+  if ((rc = dout.init(ctx, out, words * 8))) return rc;
+  P2V_LAUNCH(ctx, k_field_op, p2v_grid_for(ctx, n, 128, 8), 128, 0, op, da.as<u64>(), db.as<u64>(), dout.as<u64>(), n);
+  if ((rc = dout.finish())) return rc;
+  if (dout.host) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return P2V_OK;
+}
+
 // ---- measurement helper -------------------------------------------------------------------
 int p2v_int_pipe_peak(p2v_ctx *ctx, int mode, double *ops_per_s) {
-  if (!ctx || !ops_per_s || mode < 0 || mode > 12) return p2v_fail(ctx, P2V_E_INVALID, "p2v_int_pipe_peak: bad argument");
+  if (!ctx || !ops_per_s || mode < 0 || mode > 15) return p2v_fail(ctx, P2V_E_INVALID, "p2v_int_pipe_peak: bad argument");
   P2V_CUDA(ctx, cudaSetDevice(ctx->device));
   u64 *d = nullptr;
   P2V_CUDA(ctx, cudaMalloc(&d, 8));
@@ -275,7 +309,10 @@ int p2v_int_pipe_peak(p2v_ctx *ctx, int mode, double *ops_per_s) {
       case 9: P2V_LAUNCH(ctx, k_int_pipe<9>, grid, block, 0, d, iters, 12345u); break;
       case 10: P2V_LAUNCH(ctx, k_int_pipe<10>, grid, block, 0, d, iters, 12345u); break;
       case 11: P2V_LAUNCH(ctx, k_int_pipe<11>, grid, block, 0, d, iters, 12345u); break;
-      default: P2V_LAUNCH(ctx, k_int_pipe<12>, grid, block, 0, d, iters, 12345u); break;
+      case 12: P2V_LAUNCH(ctx, k_int_pipe<12>, grid, block, 0, d, iters, 12345u); break;
+      case 13: P2V_LAUNCH(ctx, k_int_pipe<13>, grid, block, 0, d, iters, 12345u); break;
+      case 14: P2V_LAUNCH(ctx, k_int_pipe<14>, grid, block, 0, d, iters, 12345u); break;
+      default: P2V_LAUNCH(ctx, k_int_pipe<15>, grid, block, 0, d, iters, 12345u); break;
     }
     P2V_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     P2V_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));

@@ -17,6 +17,28 @@ __global__ void __launch_bounds__(256) k_poseidon_permute(const u64 *__restrict_
   }
 }
 
+// K1 in the dual form: a thread permutes states t and t + ceil(n/2) (poseidon_permute2); an odd n lets the last thread
+// permute its first state twice.
+__global__ void __launch_bounds__(128) k_poseidon_permute2(const u64 *__restrict__ in, u64 *__restrict__ out, size_t n) {
+  size_t half = (n + 1) / 2;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < half; t += stride) {
+    size_t t2 = t + half < n ? t + half : t;
+    u64 a[12], b[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      a[i] = in[(size_t)i * n + t];
+      b[i] = in[(size_t)i * n + t2];
+    }
+    poseidon_permute2(a, b);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      out[(size_t)i * n + t] = gl_canon(a[i]);
+      if (t2 != t) out[(size_t)i * n + t2] = gl_canon(b[i]);
+    }
+  }
+}
+
 // Sponge over a strided column of words: word j of item t is at base[j*stride + t].
 // `sponge`, Hash/Sponge.hs:26-31: overwrite mode, rate 8, no padding, w = 0 -> zero digest.
 // Returns the state; digest = s[0..3] (lazy).
@@ -169,7 +191,7 @@ __global__ void __launch_bounds__(256) k_int_pipe(u64 *out, u32 iters, u32 seed)
     a[i] = (u64)x * (i + 3) + i;
     b[i] = x * (i + 7);
   }
-  if (MODE >= 10) {
+  if (MODE >= 10 && MODE != 13 && MODE != 15) {
 #pragma unroll
     for (int i = 0; i < 8; i++) a[i] = 0x3FF0000000000000ULL | (a[i] & 0xFFFFFFFFFULL);  // doubles in [1,2)
   }
@@ -204,8 +226,16 @@ __global__ void __launch_bounds__(256) k_int_pipe(u64 *out, u32 iters, u32 seed)
         } else if (MODE == 11) {  // DFMA + IMAD32 + LOP3: three pipes
           asm volatile("{.reg .f64 d; mov.b64 d,%0; fma.rn.f64 d,d,0d3FF0000000000001,0d3FF8000000000000; mov.b64 %0,d;}" : "+l"(a[i]));
           asm volatile("{.reg .u32 t; xor.b32 t,%0,%1; mul.lo.u32 %0,t,%1;}" : "+r"(b[i]) : "r"(x));
-        } else {                  // DADD only
+        } else if (MODE == 12) {  // DADD only
           asm volatile("{.reg .f64 d; mov.b64 d,%0; add.rn.f64 d,d,0d3FF8000000000000; mov.b64 %0,d;}" : "+l"(a[i]));
+        } else if (MODE == 13) {  // I2F.F64.U32 + LOP3 (which pipe converts, and how fast?)
+          asm volatile("{.reg .f64 d; .reg .u32 lo,hi; cvt.rn.f64.u32 d,%0; mov.b64 {lo,hi},d; xor.b32 %0,lo,hi;}" : "+r"(b[i]));
+        } else if (MODE == 14) {  // I2F.F64.U32 + LOP3 next to an independent DFMA chain
+          asm volatile("{.reg .f64 d; .reg .u32 lo,hi; cvt.rn.f64.u32 d,%0; mov.b64 {lo,hi},d; xor.b32 %0,lo,hi;}" : "+r"(b[i]));
+          asm volatile("{.reg .f64 d; mov.b64 d,%0; fma.rn.f64 d,d,0d3FF0000000000001,0d3FF8000000000000; mov.b64 %0,d;}" : "+l"(a[i]));
+        } else {                  // 15: I2F.F64.U32 + LOP3 next to an independent IMAD.WIDE chain
+          asm volatile("{.reg .f64 d; .reg .u32 lo,hi; cvt.rn.f64.u32 d,%0; mov.b64 {lo,hi},d; xor.b32 %0,lo,hi;}" : "+r"(b[i]));
+          asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi},%0; mul.wide.u32 %0,lo,hi;}" : "+l"(a[i]) : "r"(x));
         }
       }
     }
@@ -215,3 +245,45 @@ __global__ void __launch_bounds__(256) k_int_pipe(u64 *out, u32 iters, u32 seed)
   for (int i = 0; i < 8; i++) acc += a[i] + b[i];
   if (acc == 0x1234567812345678ULL) out[0] = acc;  // keep the chains alive
 }
+
+// Test hook (p2v_debug_field_op): the device field routines of gl.cuh one by one on caller-chosen operands, so that the
+// lazy-representation edge values (0, 1, p-1, p, p+1, 2^64-1, 2^32+-1) reach every routine directly and `inv 0 = 0`
+// (Algebra/Goldilocks.hs:155, GoldilocksExt.hs:75-80) is tested on the GPU.  Outputs are canonical.
+__global__ void k_field_op(int op, const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *__restrict__ out, size_t n) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    if (op < 16) {
+      u64 x = a[t], y = b ? b[t] : 0, r = 0;
+      switch (op) {
+        case 0: r = gl_add(x, y); break;
+        case 1: r = gl_sub(x, y); break;
+        case 2: r = gl_mul(x, y); break;
+        case 3: r = gl_inv(x); break;
+        case 4: r = gl_neg(x); break;
+        case 5: r = gl_mul_small(x, (u32)y); break;
+        case 6: r = gl_reduce128(x, y); break;
+        case 7: r = gl_pow(x, y); break;
+        case 8: r = x; break;
+        default: r = poseidon_sbox(x); break;
+      }
+      out[t] = gl_canon(r);
+    } else {
+      gl2 x = gl2_make(a[t], a[n + t]), y = b ? gl2_make(b[t], b[n + t]) : gl2_make(0, 0), r = gl2_make(0, 0);
+      switch (op) {
+        case 16: r = gl2_mul(x, y); break;
+        case 17: r = gl2_inv(x); break;
+        case 18: r = gl2_add(x, y); break;
+        case 19: r = gl2_sub(x, y); break;
+        case 20: r = gl2_sqr(x); break;
+        case 21: r = gl2_scale(y.a, x); break;
+        case 22: r = gl2_mul_x(x); break;
+        case 23: r = gl2_pow(x, y.a); break;
+        default: r = gl2_neg(x); break;
+      }
+      r = gl2_canon(r);
+      out[t] = r.a;
+      out[n + t] = r.b;
+    }
+  }
+}
+

@@ -10,12 +10,13 @@
 // (p2v_int_pipe_peak), IMAD.WIDE.U32 issues every 4 cycles per SM sub-partition, a 32-bit IMAD every 2 (like an
 // ALU op), a DFMA every 2 on a pipe of its own.  A 64x64 mulmod needs 4 IMAD.WIDE + ~13 other instructions, so the
 // 22 mulmods per round of the "fast" partial form cost far more FMA-pipe time than a dense layer made of
-// small-constant multiply-adds that never need a wide multiply.  Three generations of that layer live here, all
+// small-constant multiply-adds that never need a wide multiply.  Several generations of that layer live here, all
 // bit-exact (tests/test_gpu_hash.py), selected by POSEIDON_MDS_F64:
 //   0  poseidon_mds        22/22/20-bit limbs, 3 x 144 carry-free 32-bit IMADs
 //   1  poseidon_mds_f64    32-bit halves as doubles, 2 x 144 exact DFMAs (the FP64 pipe is otherwise idle)
 //   2  poseidon_mds_mixed  low 43 bits: 144 DFMAs, high 21 bits: 144 IMADs (two pipes)
-//   3  poseidon_mds_crt    (default) the same split after a CRT step on the circulant: 2 x 72 multiply-adds
+//   3  poseidon_mds_crt    the same split after a CRT step on the circulant: 2 x 72 multiply-adds (round-1 default)
+//   4  poseidon_mds_crt64  (default) CRT layer entirely on the FP64 pipe, 32/32 split, halved coefficients, mask-free fold
 // The fast-partial tables are still used by the PoseidonGate constraint program (constraints.cuh), as in the
 // reference.
 //
@@ -24,6 +25,10 @@
 #include "gl.cuh"
 #include "poseidon_constants.h"
 
+#ifndef P2V_DUAL
+/* 1: the kernels that hash many independent items (K1, K6a) give every thread TWO of them (poseidon_permute2) */
+#define P2V_DUAL 0
+#endif
 #ifndef POSEIDON_SBOX_GROUP
 /* s-boxes per iteration of the register-rotating loop of a full round: 3, 4, 6 or 12 (= no loop, no rotation moves).
  * With the 80-register budget of the Merkle kernel the fully unrolled form measured best (12: 82.3% of the roofline,
@@ -353,17 +358,220 @@ __device__ __forceinline__ void poseidon_mds_crt(u64 (&s)[12], int next_round) {
   poseidon_crt_row<0>(s, xp, xm, hp, hm, lo[0], hi[0], next_round);
 }
 
+// ---- CRT layer entirely on the FP64 pipe (POSEIDON_MDS_F64 == 4) ------------------------------------------------
+// Round 2.  ncu of the mixed CRT layer: the FMA pipe is the throttle (IMAD.WIDE holds it 4 cycles, the 72 IMADs of the
+// high part and the adds ptxas parks there another 280 cycles per layer) while the FP64 pipe idles at 24%.  This form
+// takes the integer multiply-adds out of the layer altogether:
+//   * 32/32 split, free on a register pair: b = hiloint2double(0x43300000, word) = 2^52 + word (exact);
+//   * the CRT butterfly absorbs the bias:  xm_j = b_j - b_{j+6},  xp_j = (b_j - 2^53) + b_{j+6}  (all exact), 18 DADDs
+//     per part instead of 12 conversions + 12 butterfly adds;
+//   * p_d and q_d are all even, so the halved coefficients p/2 = (15,14,40,17,18,24), q/2 = (2,1,1,-1,-16,4) give
+//     y_i = S'_i + D'_i, y_{i+6} = S'_i - D'_i directly (no halving step, one bit more headroom);
+//   * the seeds carry the round constants, the 2^52 "magic" that leaves the integer in the mantissa, and a constant that
+//     cancels the exponent bits of the raw high words (below), so the result words come out of the register pairs of
+//     T = S' + D' and U = S' - D' without a mask:  s0 + d0 = a, s0 - d0 = b with  a = rc_i + c, b = rc_{i+6} + c (mod p)
+//     split into 32-bit parts of equal parity (b is moved by multiples of p and by 2^32 between its parts until they
+//     match; both stay non-negative);
+//   * fold: raw words (Ll, K + Lh), (Hl, K + Hh), K = 0x43300000:  value = Ll + 2^32 (Lh + Hl) + 2^64 Hh =
+//     raw - K (2^32 + 2^64); c = -K (2^32 + 2^64) mod p sits in the seeds, so the fold works on the raw words:
+//     w1 = RL + Hl, w2 = RH + carry (< 2^31), result = (w1 + w2 : Ll) - w2 with one wrap fix-up: 8 ALU instructions.
+// Bounds: word sums <= 272 (2^32 - 1) + 2^34 < 2^41: exact in doubles, high field of T below 2^20.
+#ifndef POSEIDON_CVT_I2F
+#define POSEIDON_CVT_I2F 1
+#endif
+#define POSEIDON_MDS_PH {15, 14, 40, 17, 18, 24}
+#define POSEIDON_MDS_QH {2, 1, 1, -1, -16, 4}
+#define P2V_F64_K 0x43300000u
+struct PoseidonRcCrt64 {
+  double sl[31][6], dl[31][6], sh[31][6], dh[31][6];
+};
+constexpr u64 poseidon_addmod_c(u64 a, u64 b) {  // a, b < p
+  u64 r = a + b;
+  return (r < a || r >= GL_P) ? r - GL_P : r;
+}
+constexpr PoseidonRcCrt64 poseidon_make_rc_crt64() {
+  constexpr u64 rc[360] = P2V_ALL_ROUND_CONSTANTS;
+  constexpr u64 kadj = ((u64)P2V_F64_K << 33) - (u64)P2V_F64_K;  // K 2^32 + K 2^64 = K 2^33 - K (mod p), < p
+  constexpr u64 cadj = GL_P - kadj;
+  PoseidonRcCrt64 t{};
+  for (int r = 0; r < 31; r++)
+    for (int i = 0; i < 6; i++) {
+      u64 ra = r < 30 ? rc[r * 12 + i] : 0, rb = r < 30 ? rc[r * 12 + i + 6] : 0;
+      if (ra >= GL_P) ra -= GL_P;
+      if (rb >= GL_P) rb -= GL_P;
+      u64 a = poseidon_addmod_c(ra, cadj), b = poseidon_addmod_c(rb, cadj);
+      u64 alo = a & 0xFFFFFFFFULL, ahi = a >> 32, blo = b & 0xFFFFFFFFULL, bhi = b >> 32;
+      bool flo = ((alo ^ blo) & 1) != 0, fhi = ((ahi ^ bhi) & 1) != 0;
+      // value-preserving moves (mod p): m1 = (+1, +2^32-1) adds p; m2 = (+2^32, -1)
+      if (flo && fhi) { blo += 1; bhi += 0xFFFFFFFFULL; }
+      else if (flo) { blo += 1 + (1ULL << 32); bhi += 0xFFFFFFFEULL; }
+      else if (fhi) {
+        if (bhi >= 1) { blo += 1ULL << 32; bhi -= 1; }
+        else { blo += 2 + (1ULL << 32); bhi += 2 * 0xFFFFFFFFULL - 1; }
+      }
+      t.sl[r][i] = P2V_TWO52 + (double)((alo + blo) / 2);
+      t.dl[r][i] = (double)(((long long)alo - (long long)blo) / 2);
+      t.sh[r][i] = P2V_TWO52 + (double)((ahi + bhi) / 2);
+      t.dh[r][i] = (double)(((long long)ahi - (long long)bhi) / 2);
+    }
+  return t;
+}
+static __constant__ PoseidonRcCrt64 c_rc64 = poseidon_make_rc_crt64();
+
+// contribution of input pair J to rows I..5 (column-major: a pair can be accumulated as soon as its two s-boxes are done)
+template <int J, int I>
+__device__ __forceinline__ void poseidon_crt64_col(double (&SL)[6], double (&DL)[6], double (&SH)[6], double (&DH)[6], double xpL,
+                                                   double xmL, double xpH, double xmH) {
+  constexpr int Pc[6] = POSEIDON_MDS_PH;
+  constexpr int Qc[6] = POSEIDON_MDS_QH;
+  constexpr int d = (J - I + 12) % 12;
+  constexpr double pc = (double)Pc[d % 6];
+  constexpr double qc = (double)(d < 6 ? Qc[d] : -Qc[d - 6]);
+  SL[I] = fma(xpL, pc, SL[I]);
+  DL[I] = fma(xmL, qc, DL[I]);
+  SH[I] = fma(xpH, pc, SH[I]);
+  DH[I] = fma(xmH, qc, DH[I]);
+  if constexpr (I + 1 < 6) poseidon_crt64_col<J, I + 1>(SL, DL, SH, DH, xpL, xmL, xpH, xmH);
+}
+// biased butterfly of the pair (x_J, x_{J+6}) and its accumulation
+template <int J>
+__device__ __forceinline__ void poseidon_crt64_pair(u64 xj, u64 xk, double (&SL)[6], double (&DL)[6], double (&SH)[6], double (&DH)[6]) {
+#if POSEIDON_CVT_I2F
+  // conversion instruction (I2F.F64.U32) instead of the register-pair trick: no (word, 0x43300000) pairs to assemble
+  double bjl = __uint2double_rn((u32)xj), bjh = __uint2double_rn((u32)(xj >> 32));
+  double bkl = __uint2double_rn((u32)xk), bkh = __uint2double_rn((u32)(xk >> 32));
+  double xmL = bjl - bkl, xmH = bjh - bkh;
+  double xpL = bjl + bkl, xpH = bjh + bkh;
+#else
+  double bjl = __hiloint2double((int)P2V_F64_K, (int)(u32)xj), bjh = __hiloint2double((int)P2V_F64_K, (int)(u32)(xj >> 32));
+  double bkl = __hiloint2double((int)P2V_F64_K, (int)(u32)xk), bkh = __hiloint2double((int)P2V_F64_K, (int)(u32)(xk >> 32));
+  double xmL = bjl - bkl, xmH = bjh - bkh;
+  double xpL = (bjl - 2.0 * P2V_TWO52) + bkl, xpH = (bjh - 2.0 * P2V_TWO52) + bkh;
+#endif
+  poseidon_crt64_col<J, 0>(SL, DL, SH, DH, xpL, xmL, xpH, xmH);
+}
+__device__ __forceinline__ u64 poseidon_crt64_fold(double TL, double TH) {
+  u32 Ll = (u32)__double2loint(TL), RL = (u32)__double2hiint(TL), Hl = (u32)__double2loint(TH), RH = (u32)__double2hiint(TH);
+  u32 r0, r1;
+  asm("{\n\t.reg .u32 w2,c;\n\t"
+      "add.cc.u32 %1,%3,%4;\n\taddc.u32 w2,%5,0;\n\t"
+      "add.cc.u32 %1,%1,w2;\n\taddc.u32 c,0,0;\n\t"
+      "add.u32 w2,w2,c;\n\tadd.u32 %1,%1,c;\n\t"
+      "sub.cc.u32 %0,%2,w2;\n\tsubc.u32 %1,%1,0;\n\t}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"(Ll), "r"(RL), "r"(Hl), "r"(RH));
+  return ((u64)r1 << 32) | r0;
+}
+__device__ __forceinline__ void poseidon_crt64_seed(double (&SL)[6], double (&DL)[6], double (&SH)[6], double (&DH)[6], int next_round) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    SL[i] = c_rc64.sl[next_round][i];
+    DL[i] = c_rc64.dl[next_round][i];
+    SH[i] = c_rc64.sh[next_round][i];
+    DH[i] = c_rc64.dh[next_round][i];
+  }
+}
+// x0 = the value of lane 0 that entered the layer (for the +8 on the diagonal)
+__device__ __forceinline__ void poseidon_crt64_finish(u64 (&s)[12], u64 x0, const double (&SL)[6], const double (&DL)[6],
+                                                      const double (&SH)[6], const double (&DH)[6]) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    double TL = SL[i] + DL[i], UL = SL[i] - DL[i], TH = SH[i] + DH[i], UH = SH[i] - DH[i];
+    if (i == 0) {
+#if POSEIDON_CVT_I2F
+      double l0 = __uint2double_rn((u32)x0), h0 = __uint2double_rn((u32)(x0 >> 32));
+#else
+      double l0 = __hiloint2double((int)P2V_F64_K, (int)(u32)x0) - P2V_TWO52, h0 = __hiloint2double((int)P2V_F64_K, (int)(u32)(x0 >> 32)) - P2V_TWO52;
+#endif
+      TL = fma(l0, 8.0, TL);
+      TH = fma(h0, 8.0, TH);
+    }
+    s[i] = poseidon_crt64_fold(TL, TH);
+    s[i + 6] = poseidon_crt64_fold(UL, UH);
+  }
+}
+// the whole layer; pair 0 (the one lane 0 of a partial round feeds) is accumulated last
+__device__ __forceinline__ void poseidon_mds_crt64(u64 (&s)[12], int next_round) {
+  double SL[6], DL[6], SH[6], DH[6];
+  poseidon_crt64_seed(SL, DL, SH, DH, next_round);
+  poseidon_crt64_pair<1>(s[1], s[7], SL, DL, SH, DH);
+  poseidon_crt64_pair<2>(s[2], s[8], SL, DL, SH, DH);
+  poseidon_crt64_pair<3>(s[3], s[9], SL, DL, SH, DH);
+  poseidon_crt64_pair<4>(s[4], s[10], SL, DL, SH, DH);
+  poseidon_crt64_pair<5>(s[5], s[11], SL, DL, SH, DH);
+  poseidon_crt64_pair<0>(s[0], s[6], SL, DL, SH, DH);
+  poseidon_crt64_finish(s, s[0], SL, DL, SH, DH);
+}
+// full round with the s-boxes and the layer in ONE basic block: the FP64/ALU work of a pair is independent of the
+// s-boxes still to come, so ptxas can interleave it with their wide multiplies (POSEIDON_SPLIT_ROUNDS)
+__device__ __forceinline__ void poseidon_full_round_crt64(u64 (&s)[12], int next_round) {
+  double SL[6], DL[6], SH[6], DH[6];
+  poseidon_crt64_seed(SL, DL, SH, DH, next_round);
+  u64 x0 = 0;
+#define P2V_FR_PAIR(J)                                             \
+  {                                                                \
+    u64 a = poseidon_sbox(s[J]), b = poseidon_sbox(s[J + 6]);      \
+    if (J == 0) x0 = a;                                            \
+    poseidon_crt64_pair<J>(a, b, SL, DL, SH, DH);                  \
+  }
+  P2V_FR_PAIR(1) P2V_FR_PAIR(2) P2V_FR_PAIR(3) P2V_FR_PAIR(4) P2V_FR_PAIR(5) P2V_FR_PAIR(0)
+#undef P2V_FR_PAIR
+  poseidon_crt64_finish(s, x0, SL, DL, SH, DH);
+}
+
 #ifndef POSEIDON_MDS_SEPARATE_OUT
 #define POSEIDON_MDS_SEPARATE_OUT 0
 #endif
 #ifndef POSEIDON_MDS_F64
-#define POSEIDON_MDS_F64 3
+#define POSEIDON_MDS_F64 4
 #endif
 
 // The permutation.  Input: lazy u64 (any values); output: lazy u64 (apply gl_canon before use as data).
+#ifndef POSEIDON_SPLIT_ROUNDS
+#define POSEIDON_SPLIT_ROUNDS 1
+#endif
+__device__ __forceinline__ void poseidon_mds_layer(u64 (&s)[12], int next_round) {
+#if POSEIDON_MDS_F64 == 4
+  poseidon_mds_crt64(s, next_round);
+#elif POSEIDON_MDS_F64 == 3
+  poseidon_mds_crt(s, next_round);
+#elif POSEIDON_MDS_F64 == 2
+  poseidon_mds_mixed(s, next_round);
+#elif POSEIDON_MDS_F64
+  poseidon_mds_f64(s, next_round);
+#else
+  poseidon_mds(s, next_round);
+#endif
+}
 __device__ __forceinline__ void poseidon_permute(u64 (&s)[12]) {
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], c_pt.rc[0][i]);
+#if POSEIDON_SPLIT_ROUNDS
+  // Two loop bodies instead of one with a branch: a full round (12 s-boxes + layer in one basic block, so that the layer's
+  // FP64/ALU work is scheduled into the shadow of the wide multiplies) and a partial round.
+#pragma unroll 1
+  for (int ph = 0; ph < 3; ph++) {
+    if (ph != 1) {
+      int r0 = ph ? 26 : 0;
+#pragma unroll 1
+      for (int r = r0; r < r0 + 4; r++) {
+#if POSEIDON_MDS_F64 == 4
+        poseidon_full_round_crt64(s, r + 1);
+#else
+#pragma unroll
+        for (int k = 0; k < 12; k++) s[k] = poseidon_sbox(s[k]);
+        poseidon_mds_layer(s, r + 1);
+#endif
+      }
+    } else {
+#pragma unroll 1
+      for (int r = 4; r < 26; r++) {
+        s[0] = poseidon_sbox(s[0]);
+        poseidon_mds_layer(s, r + 1);
+      }
+    }
+  }
+#else
 #pragma unroll 1
   for (int r = 0; r < 30; r++) {
     if (r < 4 || r >= 26) {
@@ -382,14 +590,52 @@ __device__ __forceinline__ void poseidon_permute(u64 (&s)[12]) {
     } else {
       s[0] = poseidon_sbox(s[0]);
     }
-#if POSEIDON_MDS_F64 == 3
-    poseidon_mds_crt(s, r + 1);
-#elif POSEIDON_MDS_F64 == 2
-    poseidon_mds_mixed(s, r + 1);
-#elif POSEIDON_MDS_F64
-    poseidon_mds_f64(s, r + 1);
-#else
-    poseidon_mds(s, r + 1);
+    poseidon_mds_layer(s, r + 1);
+  }
 #endif
+}
+
+// ---- two permutations per thread, half a round out of phase (POSEIDON dual form, round 2) -----------------------
+// ncu of the single form: a warp issues in order, and the s-box phases are dependent carry chains on the FMA pipe —
+// the lane-0 s-box of a partial round issued 6.6% of its cycles per warp (19% of the kernel's time for 7% of its
+// instructions), the twelve s-boxes of a full round 14%, the linear layer 28%.  Relieving the FMA pipe alone (layer on
+// FP64) moved the kernel by 3%: what is missing is independent work NEXT to the chains in each warp's own instruction
+// stream.  Here a thread carries two states A and B and runs A's linear layer L_r in the same basic block as B's s-box
+// S_r, then A's S_{r+1} next to B's L_r:  FMA-pipe chains of one hash are interleaved by ptxas with the FP64/ALU
+// work of the other, statically, and every block has two independent dependency chains.  Only one hash is inside a
+// layer at any time, so the cost is one more state (24 registers), not a second set of accumulators.
+//   slot 2r+1: A.L_r || B.S_r        slot 2r+2: A.S_{r+1} || B.L_r       (prologue A.S_0)
+// The eleven other s-boxes of a full round run in a block of their own (eleven independent chains).
+__device__ __forceinline__ void poseidon_permute2(u64 (&a)[12], u64 (&b)[12]) {
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    a[i] = gl_add(a[i], c_pt.rc[0][i]);
+    b[i] = gl_add(b[i], c_pt.rc[0][i]);
+  }
+#pragma unroll
+  for (int k = 0; k < 12; k++) a[k] = poseidon_sbox(a[k]);  // A.S_0
+#pragma unroll 1
+  for (int r = 0; r < 30; r++) {
+    const bool full_b = r < 4 || r >= 26;                       // kind of B.S_r
+    const bool full_a = (r + 1 < 4 || r + 1 >= 26) && r < 29;   // kind of A.S_{r+1} (none after the last round)
+    {  // A.L_r || B.S_r (lane 0)
+      u64 t = poseidon_sbox(b[0]);
+      poseidon_mds_layer(a, r + 1);
+      b[0] = t;
+    }
+    if (full_b) {
+#pragma unroll
+      for (int k = 1; k < 12; k++) b[k] = poseidon_sbox(b[k]);
+    }
+    {  // A.S_{r+1} (lane 0) || B.L_r ; after the last round A is finished: the s-box result is dropped (one select)
+      u64 t = poseidon_sbox(a[0]);
+      poseidon_mds_layer(b, r + 1);
+      a[0] = r == 29 ? a[0] : t;
+    }
+    if (full_a) {
+#pragma unroll
+      for (int k = 1; k < 12; k++) a[k] = poseidon_sbox(a[k]);
+    }
   }
 }
+

@@ -1,0 +1,210 @@
+// C-ABI entry points for the multi-GPU form of the path (BASELINE config 5): every proof is
+// independent, so a batch is cut into contiguous slices, one per rank (one process per GPU); each rank runs the whole
+// verifier on its slice and the ONLY exchange is one all-gather of the packed accept bitmap.
+//
+//   p2v_shard_*               the slicing rule (multiples of 32 proofs, so bitmap words never straddle two ranks)
+//   p2v_nccl_unique_id/init   bootstrap of a communicator for callers that have none (a Haskell or C host, bench.py)
+//   p2v_nccl_attach           use a communicator the caller already owns
+//   p2v_verify_batch_sharded  verifyProof on the slice + ncclAllGather on the context's stream (in place)
+//
+// NCCL is bound at run time (dlopen "libnccl.so.2"): inside a torch process that is the copy torch already loaded,
+// elsewhere the system library; libp2v.so itself loads on machines without NCCL and the single-GPU API is unaffected.
+#include <dlfcn.h>
+#include <string.h>
+#include <mutex>
+#include "ctx.hpp"
+
+namespace {
+
+// the part of nccl.h this file needs (NCCL 2.x ABI: ncclUniqueId is 128 opaque bytes passed by value)
+struct NcclUniqueId {
+  char internal[128];
+};
+typedef void *NcclComm;
+enum { NCCL_UINT32 = 3 };
+struct NcclApi {
+  void *handle = nullptr;
+  int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+  int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  int (*CommCount)(NcclComm, int *) = nullptr;
+  int (*CommUserRank)(NcclComm, int *) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  int (*GetVersion)(int *) = nullptr;
+  std::string why;
+};
+
+NcclApi &nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) {
+      api.why = std::string("libnccl.so.2 could not be loaded: ") + dlerror();
+      return;
+    }
+    auto sym = [&](const char *s) {
+      void *p = dlsym(api.handle, s);
+      if (!p && api.why.empty()) api.why = std::string("libnccl lacks ") + s;
+      return p;
+    };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.CommCount = (decltype(api.CommCount))sym("ncclCommCount");
+    api.CommUserRank = (decltype(api.CommUserRank))sym("ncclCommUserRank");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+  });
+  return api;
+}
+
+int ncclReady(p2v_ctx *ctx) {
+  NcclApi &a = nccl();
+  if (!a.why.empty()) return p2v_fail(ctx, P2V_E_UNSUPPORTED, a.why);
+  return P2V_OK;
+}
+
+#define P2V_NCCL(ctx, call)                                                                                       \
+  do {                                                                                                            \
+    int r__ = (call);                                                                                             \
+    if (r__ != 0) return p2v_fail((ctx), P2V_E_CUDA, std::string(#call) + ": " + nccl().GetErrorString(r__));     \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+size_t p2v_shard_slice_len(size_t n_total, int world) {
+  if (world < 1) return 0;
+  size_t per = (n_total + (size_t)world - 1) / (size_t)world;
+  return (per + 31) / 32 * 32;
+}
+
+int p2v_shard_bounds(size_t n_total, int rank, int world, size_t *start, size_t *stop) {
+  if (world < 1 || rank < 0 || rank >= world || !start || !stop) return P2V_E_INVALID;
+  size_t per = p2v_shard_slice_len(n_total, world);
+  size_t s = (size_t)rank * per;
+  if (s > n_total) s = n_total;
+  size_t e = s + per;
+  if (e > n_total) e = n_total;
+  *start = s;
+  *stop = e;
+  return P2V_OK;
+}
+
+int p2v_nccl_unique_id(void *out128) {
+  if (!out128) return p2v_fail(nullptr, P2V_E_INVALID, "p2v_nccl_unique_id: NULL argument");
+  int rc = ncclReady(nullptr);
+  if (rc) return rc;
+  NcclUniqueId id;
+  P2V_NCCL(nullptr, nccl().GetUniqueId(&id));
+  memcpy(out128, id.internal, sizeof id.internal);
+  return P2V_OK;
+}
+
+int p2v_nccl_finalize(p2v_ctx *ctx) {
+  if (!ctx) return P2V_E_INVALID;
+  if (ctx->nccl_comm && ctx->nccl_owned) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    nccl().CommDestroy((NcclComm)ctx->nccl_comm);
+  }
+  ctx->nccl_comm = nullptr;
+  ctx->nccl_owned = false;
+  ctx->nccl_rank = 0;
+  ctx->nccl_world = 1;
+  return P2V_OK;
+}
+
+int p2v_nccl_init(p2v_ctx *ctx, const void *id128, int rank, int world) {
+  if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return p2v_fail(ctx, P2V_E_INVALID, "p2v_nccl_init: bad argument");
+  int rc = ncclReady(ctx);
+  if (rc) return rc;
+  p2v_nccl_finalize(ctx);
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  NcclUniqueId id;
+  memcpy(id.internal, id128, sizeof id.internal);
+  NcclComm comm = nullptr;
+  P2V_NCCL(ctx, nccl().CommInitRank(&comm, world, id, rank));
+  ctx->nccl_comm = comm;
+  ctx->nccl_owned = true;
+  ctx->nccl_rank = rank;
+  ctx->nccl_world = world;
+  return P2V_OK;
+}
+
+int p2v_nccl_attach(p2v_ctx *ctx, void *nccl_comm) {
+  if (!ctx || !nccl_comm) return p2v_fail(ctx, P2V_E_INVALID, "p2v_nccl_attach: NULL argument");
+  int rc = ncclReady(ctx);
+  if (rc) return rc;
+  int world = 0, rank = -1;
+  P2V_NCCL(ctx, nccl().CommCount((NcclComm)nccl_comm, &world));
+  P2V_NCCL(ctx, nccl().CommUserRank((NcclComm)nccl_comm, &rank));
+  p2v_nccl_finalize(ctx);
+  ctx->nccl_comm = nccl_comm;
+  ctx->nccl_owned = false;
+  ctx->nccl_rank = rank;
+  ctx->nccl_world = world;
+  return P2V_OK;
+}
+
+int p2v_nccl_info(p2v_ctx *ctx, int *rank, int *world, int *version) {
+  if (!ctx) return P2V_E_INVALID;
+  if (rank) *rank = ctx->nccl_comm ? ctx->nccl_rank : 0;
+  if (world) *world = ctx->nccl_comm ? ctx->nccl_world : 1;
+  if (version) {
+    *version = 0;
+    if (ncclReady(nullptr) == P2V_OK && nccl().GetVersion) nccl().GetVersion(version);
+  }
+  return P2V_OK;
+}
+
+// verifyProof (Plonk/Verifier.hs:56-65) over a batch of n_total proofs of which this rank holds the slice
+// [start, stop) = p2v_shard_bounds(n_total, rank, world):  blobs_local is AoS [stop - start][blob_words].
+//   accept_bits_full: world * slice_len / 32 words (host or device); after the call the first ceil(n_total/32) words
+//                     are the accept bitmap of the WHOLE batch, identical on every rank (padding bits are 0);
+//   status_local:     [stop - start] status words of this rank's proofs (may be NULL).
+// world == 1 needs no communicator and is exactly p2v_verify_batch.
+int p2v_verify_batch_sharded(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs_local, size_t n_total, int rank, int world,
+                             uint32_t *accept_bits_full, uint32_t *status_local) {
+  if (!ctx || !c || !accept_bits_full) return p2v_fail(ctx, P2V_E_INVALID, "p2v_verify_batch_sharded: NULL argument");
+  size_t start = 0, stop = 0;
+  if (p2v_shard_bounds(n_total, rank, world, &start, &stop) != P2V_OK) return p2v_fail(ctx, P2V_E_INVALID, "p2v_verify_batch_sharded: bad rank/world");
+  const size_t n_local = stop - start;
+  if (n_local && !blobs_local) return p2v_fail(ctx, P2V_E_INVALID, "p2v_verify_batch_sharded: blobs_local is NULL");
+  if (world > 1) {
+    if (!ctx->nccl_comm) return p2v_fail(ctx, P2V_E_INVALID, "p2v_verify_batch_sharded: no communicator (p2v_nccl_init / p2v_nccl_attach first)");
+    if (ctx->nccl_world != world || ctx->nccl_rank != rank)
+      return p2v_fail(ctx, P2V_E_INVALID, "p2v_verify_batch_sharded: rank/world differ from the communicator's");
+  }
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t words_per_rank = p2v_shard_slice_len(n_total, world) / 32;
+  const size_t words_full = words_per_rank * (size_t)world;
+  if (words_full == 0) return P2V_OK;
+  // the gathered bitmap lives on the device: the caller's buffer if it is device memory, else a pool temporary
+  DevOut full;
+  int rc;
+  if ((rc = full.init(ctx, accept_bits_full, words_full * 4))) return rc;
+  uint32_t *mine = full.as<uint32_t>() + (size_t)rank * words_per_rank;
+  // padding words of a short (or empty) last slice are zero; K7 writes ceil(n_local/32) words
+  P2V_CUDA(ctx, cudaMemsetAsync(mine, 0, words_per_rank * 4, ctx->stream));
+  if (n_local) {
+    if ((rc = p2v_verify_batch(ctx, c, blobs_local, n_local, mine, status_local))) return rc;
+  }
+  if (world > 1) {
+    // in place: rank r's words already sit at recvbuff + r * count
+    P2V_NCCL(ctx, nccl().AllGather(mine, full.as<uint32_t>(), words_per_rank, NCCL_UINT32, (NcclComm)ctx->nccl_comm, ctx->stream));
+  }
+  if ((rc = full.finish())) return rc;
+  if (full.host) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return P2V_OK;
+}
+
+}  // extern "C"

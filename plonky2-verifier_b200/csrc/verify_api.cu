@@ -123,7 +123,7 @@ struct WsAlloc {
 };
 
 // carve the per-chunk planes out of one allocation
-size_t carve(const DevCircuit &d, size_t m, char *base, Workspace *ws, bool want_folded) {
+size_t carve(const DevCircuit &d, size_t m, char *base, Workspace *ws, bool want_folded, bool want_roots = false) {
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -141,7 +141,9 @@ size_t carve(const DevCircuit &d, size_t m, char *base, Workspace *ws, bool want
   uint8_t *tree_ok = (uint8_t *)take((size_t)(4 + d.nsteps) * d.Q * m);
   u64 *folded = want_folded ? (u64 *)take((size_t)2 * d.Q * m * 8) : nullptr;
   uint8_t *eq = (uint8_t *)take(m);
+  u64 *roots = want_roots ? (u64 *)take((size_t)4 * (4 + d.nsteps) * d.Q * m * 8) : nullptr;
   if (ws) {
+    ws->roots = roots; ws->ch_in = nullptr; ws->ch_in_n = 0; ws->ch_in_off = 0;
     ws->pp = pp; ws->qp = qp; ws->ch = ch; ws->pih = pih; ws->pre = pre; ws->apow = apow; ws->comb = comb; ws->qstat = qstat;
     ws->folded = folded; ws->eqmask = eq; ws->tree_ok = tree_ok;
   }
@@ -199,6 +201,8 @@ struct Outputs {
   u32 *accept_bits = nullptr;  // ceil(n/32)
   u32 *qstatus = nullptr;      // [n][Q]
   u64 *folded = nullptr;       // SoA [2][n*Q]
+  u64 *roots = nullptr;        // SoA [(4+nsteps)*4][n*Q]
+  const u64 *challenges_in = nullptr;  // SoA [ch_words][n]: test hook, replaces the transcript's challenges
   int verdict_mode = 0;        // bit0 eqs, bit1 fri
 };
 
@@ -227,6 +231,17 @@ __global__ void k_copy_folded(const u64 *__restrict__ folded, size_t m, int Q, u
     size_t half = i / ((size_t)Q * m), rem = i - half * (size_t)Q * m;
     size_t q = rem / m, t = rem - q * m;
     dst[half * n_total * Q + (c0 + t) * Q + q] = folded[i];
+  }
+}
+__global__ void k_copy_roots(const u64 *__restrict__ roots, size_t m, int Q, int ntrees, u64 *__restrict__ dst, size_t n_total, size_t c0) {
+  // src [4][ntrees*Q*m] with t = tr*Q*m + q*m + p ; dst [(tr*4+i)][n_total*Q] with index p*Q + q
+  size_t per = (size_t)ntrees * Q * m, total = 4 * per;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride) {
+    size_t i = k / per, t = k - i * per;
+    size_t tr = t / ((size_t)Q * m), rem = t - tr * (size_t)Q * m;
+    size_t q = rem / m, p = rem - q * m;
+    dst[(tr * 4 + i) * n_total * Q + (c0 + p) * Q + q] = roots[k];
   }
 }
 __global__ void k_copy_bytes(const uint8_t *__restrict__ src, size_t m, uint8_t *__restrict__ dst) {
@@ -262,6 +277,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   P2V_CUDA(ctx, cudaSetDevice(ctx->device));
   const DevCircuit &d = cir->dev;
   const size_t blob_words = (size_t)d.L.blob_words;
+  if ((blob_words + 31) / 32 > 65535) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "proof blob longer than 2^21 words (K0 tiles words along grid.y)");
   bool src_dev = p2v_is_device_ptr(blobs);
   // Chunking.  Serial mode: as few chunks as memory allows.  Pipelined mode (default): chunks go round-robin over
   // `pipeline` lanes (stream + workspace each), so K0+K4+K5 of the next chunks (latency-bound, one thread per proof)
@@ -278,18 +294,21 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   chunk = (chunk + 31) / 32 * 32;
   if (chunk > n) chunk = (n + 31) / 32 * 32;
   const int depth = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->pipeline, (n + chunk - 1) / chunk));
-  bool want_folded = out.folded != nullptr;
-  size_t ws_bytes = carve(d, chunk, nullptr, nullptr, want_folded);
+  bool want_folded = out.folded != nullptr, want_roots = out.roots != nullptr;
+  size_t ws_bytes = carve(d, chunk, nullptr, nullptr, want_folded, want_roots);
   int rc;
   Workspace wsp[P2V_MAX_DEPTH];
   for (int k = 0; k < depth; k++) {
     if ((rc = ensureWorkspace(ctx, k, ws_bytes))) return rc;
-    carve(d, chunk, (char *)(k == 0 ? ctx->ws : ctx->lane_ws[k]), &wsp[k], want_folded);
+    carve(d, chunk, (char *)(k == 0 ? ctx->ws : ctx->lane_ws[k]), &wsp[k], want_folded, want_roots);
   }
   if (!src_dev && (rc = ensureStage(ctx, chunk * blob_words * 8))) return rc;
 
   // outputs that may live on the host (temporaries are allocated in stream order on the primary stream)
-  DevOut o_ch, o_comb, o_eq, o_status, o_bits, o_qs, o_folded;
+  DevOut o_ch, o_comb, o_eq, o_status, o_bits, o_qs, o_folded, o_roots;
+  DevIn i_ch;
+  if ((rc = i_ch.init(ctx, out.challenges_in, (size_t)d.ch_words * n * 8))) return rc;
+  if ((rc = o_roots.init(ctx, out.roots, (size_t)4 * (4 + d.nsteps) * n * d.Q * 8))) return rc;
   if ((rc = o_ch.init(ctx, out.challenges, (size_t)d.ch_words * n * 8))) return rc;
   if ((rc = o_comb.init(ctx, out.combined, (size_t)2 * d.r * n * 8))) return rc;
   if ((rc = o_eq.init(ctx, out.eqmask, n))) return rc;
@@ -341,6 +360,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     int lane = k % depth;       // stream + workspace of this chunk
     cudaStream_t st = streams[lane];
     Workspace &ws = wsp[lane];
+    ws.ch_in = i_ch.as<u64>(); ws.ch_in_n = n; ws.ch_in_off = c0;
     if (!src_dev) {
       // double-buffered staging: the H2D copy of chunk k+1 overlaps the kernels of chunk k; buffer b is free
       // again once the K0 that read it (chunk k-2) has finished
@@ -355,7 +375,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     // K0
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     {
-      dim3 grid((unsigned)((blob_words + 31) / 32), (unsigned)((m + 31) / 32));
+      dim3 grid((unsigned)((m + 31) / 32), (unsigned)((blob_words + 31) / 32));
       P2V_LAUNCH_ON(ctx, st, k_stage_transpose, grid, 256, 0, src, m, (int)blob_words, d.L.proof_words, d.L.query_words, d.Q, ws.pp, ws.qp);
     }
     if (!src_dev) P2V_CUDA(ctx, cudaEventRecord(ctx->compute_done[b], st));
@@ -374,6 +394,14 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
       size_t items = m * (size_t)d.Q * (4 + d.nsteps);
       // serial mode: persistent grid of 256-thread blocks; pipelined mode: one 128-thread block per 128 openings, so
       // that blocks of all lanes' kernels interleave on the SMs as resources free up
+#if P2V_DUAL
+      {
+        size_t pairs = ((m + 1) / 2) * (size_t)d.Q * (4 + d.nsteps);
+        unsigned grid = depth >= 2 ? (unsigned)((pairs + P2V_MERKLE_DUAL_BLOCK - 1) / P2V_MERKLE_DUAL_BLOCK)
+                                   : (unsigned)p2v_grid_for(ctx, pairs, P2V_MERKLE_DUAL_BLOCK, P2V_MERKLE_DUAL_MINBLOCKS);
+        P2V_LAUNCH_ON(ctx, st, (k_fri_merkle_dual<P2V_MERKLE_DUAL_BLOCK, P2V_MERKLE_DUAL_MINBLOCKS>), grid, P2V_MERKLE_DUAL_BLOCK, 0, d, ws, m);
+      }
+#else
       if (depth >= 2) {
         unsigned grid = (unsigned)((items + P2V_MERKLE_BLOCK_PIPE - 1) / P2V_MERKLE_BLOCK_PIPE);
         P2V_LAUNCH_ON(ctx, st, (k_fri_merkle<P2V_MERKLE_BLOCK_PIPE, P2V_MERKLE_MINBLOCKS_PIPE>), grid, P2V_MERKLE_BLOCK_PIPE, 0, d, ws, m);
@@ -381,6 +409,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
         unsigned grid = (unsigned)p2v_grid_for(ctx, items, P2V_MERKLE_BLOCK, P2V_MERKLE_MINBLOCKS);
         P2V_LAUNCH_ON(ctx, st, (k_fri_merkle<P2V_MERKLE_BLOCK, P2V_MERKLE_MINBLOCKS>), grid, P2V_MERKLE_BLOCK, 0, d, ws, m);
       }
+#endif
       if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
       P2V_LAUNCH_ON(ctx, st, k_fri_query, p2v_grid_for(ctx, m * d.Q, 256, 4), 256, 0, d, ws, m);
     }
@@ -398,6 +427,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     if (o_comb.dev) P2V_LAUNCH_ON(ctx, st, k_copy_planes, p2v_grid_for(ctx, m * 2 * d.r, 256, 8), 256, 0, ws.comb, m, 2 * d.r, o_comb.as<u64>(), n, c0);
     if (o_eq.dev) P2V_LAUNCH_ON(ctx, st, k_copy_bytes, p2v_grid_for(ctx, m, 256, 8), 256, 0, ws.eqmask, m, o_eq.as<uint8_t>() + c0);
     if (o_qs.dev) P2V_LAUNCH_ON(ctx, st, k_copy_qstat, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.qstat, m, d.Q, o_qs.as<u32>(), c0);
+    if (o_roots.dev) P2V_LAUNCH_ON(ctx, st, k_copy_roots, p2v_grid_for(ctx, m * d.Q * 4 * (4 + d.nsteps), 256, 8), 256, 0, ws.roots, m, d.Q, 4 + d.nsteps, o_roots.as<u64>(), n, c0);
     if (o_folded.dev) P2V_LAUNCH_ON(ctx, st, k_copy_folded, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.folded, m, d.Q, o_folded.as<u64>(), n, c0);
   }
   if (depth >= 2) {
@@ -409,7 +439,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   }
   double host_issued = host_ms();
   bool any_host = false;
-  for (DevOut *o : {&o_ch, &o_comb, &o_eq, &o_status, &o_bits, &o_qs, &o_folded}) {
+  for (DevOut *o : {&o_ch, &o_comb, &o_eq, &o_status, &o_bits, &o_qs, &o_folded, &o_roots}) {
     if ((rc = o->finish())) return rc;
     any_host = any_host || (o->host != nullptr);
   }
@@ -572,6 +602,22 @@ int p2v_fri(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n,
   return runBatch(ctx, c, blobs, n, RUN_CHALLENGES | RUN_FRI, o);
 }
 
+int p2v_verify_intermediates(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n, const p2v_intermediates *io) {
+  if (!io) return p2v_fail(ctx, P2V_E_INVALID, "p2v_verify_intermediates: io is NULL");
+  Outputs o;
+  o.challenges_in = io->challenges_in;
+  o.challenges = io->challenges;
+  o.combined = io->combined;
+  o.eqmask = io->eq_ok_mask;
+  o.status = io->status;
+  o.accept_bits = io->accept_bits;
+  o.qstatus = io->query_status;
+  o.folded = io->folded;
+  o.roots = io->roots;
+  o.verdict_mode = 3;
+  return runBatch(ctx, c, blobs, n, RUN_CHALLENGES | RUN_CONSTRAINTS | RUN_FRI, o);
+}
+
 int p2v_verify_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n, uint32_t *accept_bits, uint32_t *status) {
   if (!accept_bits) return p2v_fail(ctx, P2V_E_INVALID, "p2v_verify_batch: accept_bits is NULL");
   Outputs o;
@@ -579,6 +625,27 @@ int p2v_verify_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, 
   o.accept_bits = accept_bits;
   o.verdict_mode = 3;
   return runBatch(ctx, c, blobs, n, RUN_CHALLENGES | RUN_CONSTRAINTS | RUN_FRI, o);
+}
+
+int p2v_stage(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n, uint64_t *planes_out) {
+  if (!ctx || !c || !blobs || !planes_out) return p2v_fail(ctx, P2V_E_INVALID, "p2v_stage: NULL argument");
+  if (c->ctx != ctx) return p2v_fail(ctx, P2V_E_INVALID, "circuit belongs to another context");
+  if (n == 0) return P2V_OK;
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  const DevCircuit &d = c->dev;
+  const size_t bw = (size_t)d.L.blob_words;
+  if ((bw + 31) / 32 > 65535) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "p2v_stage: blob longer than 2^21 words");
+  DevIn in;
+  DevOut out;
+  int rc;
+  if ((rc = in.init(ctx, blobs, n * bw * 8))) return rc;
+  if ((rc = out.init(ctx, planes_out, n * bw * 8))) return rc;
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((bw + 31) / 32));
+  u64 *pp = out.as<u64>();
+  P2V_LAUNCH(ctx, k_stage_transpose, grid, 256, 0, in.as<u64>(), n, (int)bw, d.L.proof_words, d.L.query_words, d.Q, pp, pp + (size_t)d.L.proof_words * n);
+  if ((rc = out.finish())) return rc;
+  if (out.host) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return P2V_OK;
 }
 
 int p2v_verify_groups(p2v_ctx *ctx, size_t n_groups, const p2v_circuit *const *circuits, const uint64_t *const *blobs,

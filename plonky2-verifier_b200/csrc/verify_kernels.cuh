@@ -66,6 +66,9 @@ struct Workspace {
   uint8_t *tree_ok;  // [4+nsteps][Q][n]  Merkle opening verdicts (K6a -> K6b)
   u64 *folded; // [2][Q*n]        final folded evaluation per query (debug/parity output)
   uint8_t *eqmask;  // [n]        bit j: round j of the quotient identity holds
+  u64 *roots;  // [4][(4+nsteps)*Q*n]  recomputed Merkle roots of every opening (debug/parity output, else NULL)
+  const u64 *ch_in;  // test hook: SoA [ch_words][ch_in_n] challenges that replace the transcript's (else NULL)
+  size_t ch_in_n, ch_in_off;  // plane length of ch_in and this chunk's first proof in it
 };
 
 __device__ __forceinline__ u32 bitrev(u32 x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
@@ -100,8 +103,9 @@ __global__ void __launch_bounds__(256) k_stage_transpose(const u64 *__restrict__
                                                          int query_words, int Q, u64 *__restrict__ pp, u64 *__restrict__ qp) {
   __shared__ u64 tile[32][33];
   int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  size_t p0 = (size_t)blockIdx.y * 32;
-  int w0 = blockIdx.x * 32;
+  // proof tiles run along grid.x (up to 2^31-1 blocks): grid.y is limited to 65535, i.e. ~2.09 M proofs per chunk
+  size_t p0 = (size_t)blockIdx.x * 32;
+  int w0 = blockIdx.y * 32;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     size_t p = p0 + ty + 8 * k;
@@ -221,6 +225,16 @@ __global__ void __launch_bounds__(128) k_challenges(const __grid_constant__ DevC
       nbuf = 0;
     }
   }
+  if (ws.ch_in) {
+    // test hook (p2v_verify_intermediates): verify against GIVEN challenges, so that branches no honest transcript
+    // reaches (zeta = 1 in evalLagrange0, x = zeta in combineInitial) can be compared with the oracle
+#pragma unroll 1
+    for (int w = 0; w < c.ch_words; w++) {
+      u64 v = gl_canon(ws.ch_in[(size_t)w * ws.ch_in_n + ws.ch_in_off + p]);
+      if (w >= c.ch_idx) v &= ((1ull << c.lde_bits) - 1);
+      ws.ch[(size_t)w * n + p] = v;
+    }
+  }
   // precomputeReducedOpenings, Plonk/FRI.hs:128-134: Y0 = sum alpha^i batch_this_i, Y1 over batch_next.
   // toFriOpenings order (Challenge/FRI.hs:46-61): constants, sigmas, wires, zs, partial_products,
   // quotient, lookup_zs | zs_next, lookup_zs_next.  Horner from the last element (Goldilocks.hs:180-183).
@@ -275,7 +289,7 @@ __global__ void __launch_bounds__(128) k_challenges(const __grid_constant__ DevC
 // 4 blocks of 256 per SM (64 registers, 112 B of spills, 8 warps/scheduler) 79.5%, 3 blocks (80 registers) 82.2%,
 // 2 blocks (115 registers, no spills, 4 warps/scheduler) 83.9%.
 #ifndef P2V_MERKLE_MINBLOCKS
-#define P2V_MERKLE_MINBLOCKS 2
+#define P2V_MERKLE_MINBLOCKS 3
 #endif
 #ifndef P2V_MERKLE_BLOCK
 #define P2V_MERKLE_BLOCK 256
@@ -355,6 +369,109 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) k_fri_merkle(const __grid_co
       ok = ok && (gl_canon(s[i]) == gl_canon(want));
     }
     ws.tree_ok[t] = ok ? 1 : 0;
+    if (ws.roots) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) ws.roots[(size_t)i * total + t] = gl_canon(s[i]);
+    }
+  }
+}
+
+// K6a in the dual form (P2V_DUAL): thread t = (tree, q, pair of proofs 2i, 2i+1); the two openings belong to the same tree
+// and query slot, so they take the same number of permutations and run in lockstep through poseidon_permute2.  An odd
+// chunk size lets the last pair hash proof n-1 twice (written once).
+#ifndef P2V_MERKLE_DUAL_BLOCK
+#define P2V_MERKLE_DUAL_BLOCK 128
+#endif
+#ifndef P2V_MERKLE_DUAL_MINBLOCKS
+#define P2V_MERKLE_DUAL_MINBLOCKS 3
+#endif
+template <int BLOCK, int MINBLOCKS>
+__global__ void __launch_bounds__(BLOCK, MINBLOCKS) k_fri_merkle_dual(const __grid_constant__ DevCircuit c, Workspace ws, size_t n) {
+  const int Q = c.Q;
+  const size_t half = (n + 1) / 2;
+  const size_t per_tree = n * (size_t)Q;
+  const size_t pairs_per_tree = half * (size_t)Q;
+  const size_t total = pairs_per_tree * (size_t)(4 + c.nsteps);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const u64 *__restrict__ pp = ws.pp;
+  const u64 *__restrict__ qp = ws.qp;
+  const p2v_layout &L = c.L;
+  const size_t qstride = per_tree;  // word w of (q, proof) at qp[w*Q*n + q*n + proof]
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    int tr = (int)(t / pairs_per_tree);
+    size_t rem = t - (size_t)tr * pairs_per_tree;  // = q*half + pair
+    int q = (int)(rem / half);
+    size_t pa = 2 * (rem - (size_t)q * half);
+    size_t pb = pa + 1 < n ? pa + 1 : pa;
+    const u64 *__restrict__ qa = qp + (size_t)q * n + pa;
+    const u64 *__restrict__ qb = qp + (size_t)q * n + pb;
+    u32 ia = (u32)ws.ch[(size_t)(c.ch_idx + q) * n + pa], ib = (u32)ws.ch[(size_t)(c.ch_idx + q) * n + pb];
+    int leaf_off, width, sib_off, plen, cap_off;
+    if (tr < 4) {
+      leaf_off = L.q_off_leaf[tr]; width = L.oracle_width[tr]; sib_off = L.q_off_sibs[tr]; plen = L.init_path_len;
+      cap_off = tr == 1 ? L.off_wires_cap : tr == 2 ? L.off_zs_pp_cap : L.off_quotient_cap;
+    } else {
+      int st = tr - 4;
+      leaf_off = L.q_off_step_evals[st]; width = 2 << c.arity_bits[st]; sib_off = L.q_off_step_sibs[st]; plen = L.step_path_len[st];
+      ia >>= c.cum_bits[st + 1];
+      ib >>= c.cum_bits[st + 1];
+      cap_off = L.off_commit_caps + st * L.cap_words;
+    }
+    u64 a[12], b[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) a[i] = b[i] = 0;
+    int nblk = (width + 7) >> 3;
+    int iters = nblk + plen;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+      if (it < nblk) {
+        int k = width - it * 8;
+        size_t off = (size_t)(leaf_off + it * 8) * qstride;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (i < k) {
+            a[i] = qa[off + (size_t)i * qstride];
+            b[i] = qb[off + (size_t)i * qstride];
+          }
+      } else {
+        size_t off = (size_t)(sib_off + (it - nblk) * 4) * qstride;
+        bool ea = (ia & 1u) == 0, eb = (ib & 1u) == 0;
+        ia >>= 1;
+        ib >>= 1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          u64 sa = qa[off + (size_t)i * qstride], sb = qb[off + (size_t)i * qstride];
+          u64 na = a[i], nb = b[i];
+          a[i] = ea ? na : sa;
+          a[4 + i] = ea ? sa : na;
+          a[8 + i] = 0;
+          b[i] = eb ? nb : sb;
+          b[4 + i] = eb ? sb : nb;
+          b[8 + i] = 0;
+        }
+      }
+      poseidon_permute2(a, b);
+    }
+    bool oka = ia < (1u << c.cap_height), okb = ib < (1u << c.cap_height);
+    u32 ca = oka ? ia : 0, cb = okb ? ib : 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      u64 wa = tr == 0 ? __ldg(c.vkey + ca * 4 + i) : pp[(size_t)(cap_off + ca * 4 + i) * n + pa];
+      u64 wb = tr == 0 ? __ldg(c.vkey + cb * 4 + i) : pp[(size_t)(cap_off + cb * 4 + i) * n + pb];
+      oka = oka && (gl_canon(a[i]) == gl_canon(wa));
+      okb = okb && (gl_canon(b[i]) == gl_canon(wb));
+    }
+    size_t base = (size_t)tr * per_tree + (size_t)q * n;
+    ws.tree_ok[base + pa] = oka ? 1 : 0;
+    if (pb != pa) ws.tree_ok[base + pb] = okb ? 1 : 0;
+    if (ws.roots) {
+      const size_t all = per_tree * (size_t)(4 + c.nsteps);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        ws.roots[(size_t)i * all + base + pa] = gl_canon(a[i]);
+        if (pb != pa) ws.roots[(size_t)i * all + base + pb] = gl_canon(b[i]);
+      }
+    }
   }
 }
 

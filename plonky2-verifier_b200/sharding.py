@@ -1,9 +1,18 @@
-"""Multi-GPU sharding of a proof batch.
+"""Multi-GPU sharding of a proof batch (BASELINE config 5).
 
-Every proof is independent, so the batch is cut into contiguous slices, one per rank (one process per GPU);
-each rank verifies its slice with its own Context/Circuit and the ONLY exchange is one all-gather of the packed
-accept bitmap (NCCL over NVLink on GPUs; the same code runs over gloo for the CPU tests).  Slices are multiples
-of 32 proofs so that bitmap words never straddle two ranks.
+Every proof is independent, so the batch is cut into contiguous slices, one per rank (one process per GPU); each
+rank verifies its slice with its own Context/Circuit and the ONLY exchange is one all-gather of the packed accept
+bitmap.  The product path is the C export `p2v_verify_batch_sharded` (csrc/sharded_api.cu: slice -> K0..K7 ->
+ncclAllGather on the context's stream); this module is its host-side mirror:
+
+  * `slice_len` / `shard_bounds` / `pack_bits` — the slicing rule in Python (equal to p2v_shard_*; tests compare them);
+  * `init_comm` — bootstrap of the library's NCCL communicator over an existing torch.distributed group (rank 0 makes the
+    unique id, `broadcast_object_list` ships it);
+  * `verify_batch_sharded` — the call a torch user makes; it orders the context's stream against torch's current stream
+    on both sides, so callers need no extra synchronisation (the context's stream is non-blocking);
+  * `gather_accept_bitmap` — the same gather over any torch.distributed backend (gloo in the CPU tests).
+
+Slices are multiples of 32 proofs so that bitmap words never straddle two ranks.
 """
 import numpy as np
 
@@ -31,7 +40,7 @@ def pack_bits(flags):
 
 
 def gather_accept_bitmap(local_words, n_total, dist=None, group=None):
-    """All-gather the per-rank bitmap words into the bitmap of the whole batch (torch tensors, any device).
+    """All-gather the per-rank bitmap words into the bitmap of the whole batch (torch tensors, any device/backend).
 
     local_words: int32/uint32 tensor with slice_len(n_total, world)/32 words (zero padded)."""
     import torch
@@ -47,33 +56,82 @@ def gather_accept_bitmap(local_words, n_total, dist=None, group=None):
     return out[: (n_total + 31) // 32]
 
 
-def verify_batch_sharded(circuit, blobs_local, n_total, rank, world, dist=None, group=None):
-    """Verify this rank's slice on its GPU and return (bitmap of the WHOLE batch as a device tensor, local status).
+def init_comm(ctx, dist, group=None):
+    """Collective: give `ctx` an NCCL communicator spanning the torch.distributed group (idempotent).
+    torch only carries the 128-byte unique id; the communicator itself belongs to libp2v (p2v_nccl_init)."""
+    import plonky2_verifier_b200 as p2v
 
-    blobs_local: this rank's slice (host array or device tensor), AoS [n_local][blob_words]."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    r, w, _ = ctx.nccl_info()
+    if w == world and r == rank and world > 1:
+        return rank, world
+    if world == 1:
+        return 0, 1
+    box = [p2v.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.nccl_init(box[0], rank, world)
+    return rank, world
+
+
+def verify_batch_sharded(circuit, blobs_local, n_total, rank, world, dist=None, group=None, accept_bits_full=None, status=None):
+    """Verify this rank's slice on its GPU and return (bitmap words of the WHOLE batch as a device tensor, local status
+    words as a device tensor) — `map verifyProof` over a batch that lives on `world` GPUs.
+
+    blobs_local: this rank's slice, AoS [n_local][blob_words] (host array or device tensor).
+    Stream contract (include/p2v.h): the context's stream is non-blocking, so it is made to wait for torch's current
+    stream before the call (inputs and output buffers produced there are complete) and torch's current stream waits for
+    the context's stream after it (the returned tensors may be used right away)."""
     import torch
 
+    ctx = circuit.ctx
     start, stop = shard_bounds(n_total, rank, world)
     n_local = stop - start
-    words_per_rank = slice_len(n_total, world) // 32
-    dev = torch.device("cuda", circuit.ctx.device)
-    bits = torch.zeros(words_per_rank, dtype=torch.int32, device=dev)
-    status = torch.zeros(max(n_local, 1), dtype=torch.int32, device=dev)
-    if n_local:
-        circuit.verifyProof(blobs_local, n=n_local, accept_bits=bits, status=status)
-    if dist is not None and dist.is_initialized() and world > 1:
-        # the gather is enqueued on the verifier's stream: no host synchronisation in between
-        with torch.cuda.stream(torch.cuda.ExternalStream(circuit.ctx.stream)):
-            full = gather_accept_bitmap(bits, n_total, dist, group)
-    else:
-        full = bits[: (n_total + 31) // 32]
-    return full, status[:n_local]
+    words_full = slice_len(n_total, world) // 32 * world
+    dev = torch.device("cuda", ctx.device)
+    if world > 1:
+        if dist is None or not dist.is_initialized():
+            raise ValueError("world > 1 needs an initialised torch.distributed (or call ctx.nccl_init yourself)")
+        init_comm(ctx, dist, group)
+    if accept_bits_full is None:
+        accept_bits_full = torch.empty(max(words_full, 1), dtype=torch.int32, device=dev)
+    if status is None:
+        # not ACCEPT (0): a reader that races ahead of the verifier must not see accepting verdicts
+        status = torch.full((max(n_local, 1),), -1, dtype=torch.int32, device=dev)
+    p2v_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    p2v_stream.wait_stream(torch.cuda.current_stream(dev))
+    circuit.verifyProofSharded(blobs_local, n_total, rank, world, accept_bits_full=accept_bits_full, status=status)
+    torch.cuda.current_stream(dev).wait_stream(p2v_stream)
+    return accept_bits_full[: (n_total + 31) // 32], status[:n_local]
+
+
+def _node_cpus(node):
+    cpus = set()
+    for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def host_nodes():
+    """NUMA nodes of the host that have CPUs: {node: set(cpus)}."""
+    import os
+
+    out = {}
+    try:
+        for d in sorted(os.listdir("/sys/devices/system/node")):
+            if d.startswith("node") and d[4:].isdigit():
+                cpus = _node_cpus(int(d[4:]))
+                if cpus:
+                    out[int(d[4:])] = cpus
+    except OSError:
+        pass
+    return out
 
 
 def gpu_numa_cpus(device):
-    """CPUs of the NUMA node the GPU hangs off (None if the topology cannot be read).  Pinned staging buffers
-    that are first-touched from these CPUs sit on the GPU's own node; on a two-socket host the other placement
-    halves the H2D bandwidth of the end-to-end path."""
+    """CPUs of the NUMA node sysfs reports for the GPU (None if unknown).  On some hosts every GPU reports node 0
+    (VERDICT r1): use `place_on_best_node` where the placement matters."""
     try:
         import torch
 
@@ -82,17 +140,13 @@ def gpu_numa_cpus(device):
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
         if node < 0:
             return None
-        cpus = set()
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        return cpus or None
+        return _node_cpus(node) or None
     except Exception:
         return None
 
 
 def bind_to_gpu_numa_node(device):
-    """Restrict this process to the CPUs next to `device`; returns the previous affinity (for os.sched_setaffinity)."""
+    """Restrict this process to the CPUs next to `device` per sysfs; returns the previous affinity."""
     import os
 
     prev = os.sched_getaffinity(0)
@@ -100,3 +154,68 @@ def bind_to_gpu_numa_node(device):
     if cpus and (cpus & prev):
         os.sched_setaffinity(0, cpus & prev)
     return prev
+
+
+def measure_h2d_by_node(device, mbytes=256, reps=3):
+    """MEASURED placement policy: pinned-host -> device copy bandwidth (GB/s) of `device` from a buffer that was
+    first-touched on each host NUMA node in turn -> {node: GB/s}.  The process affinity is restored afterwards."""
+    import os
+    import time
+    import torch
+
+    prev = os.sched_getaffinity(0)
+    res = {}
+    dev = torch.device("cuda", device)
+    dst = torch.empty(mbytes << 20, dtype=torch.uint8, device=dev)
+    try:
+        for node, cpus in host_nodes().items():
+            if not (cpus & prev):
+                continue
+            os.sched_setaffinity(0, cpus & prev)
+            src = torch.empty(mbytes << 20, dtype=torch.uint8, pin_memory=True)
+            src.fill_(1)  # first touch on this node
+            torch.cuda.synchronize(dev)
+            best = 0.0
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                dst.copy_(src, non_blocking=True)
+                torch.cuda.synchronize(dev)
+                best = max(best, (mbytes << 20) / (time.perf_counter() - t0) / 1e9)
+            res[node] = best
+            del src
+    finally:
+        os.sched_setaffinity(0, prev)
+    return res
+
+
+def place_on_best_node(device, rank=0, world=1):
+    """Bind this process (and therefore the pinned staging buffers it first-touches) to the host NUMA node from which
+    `device` measured the highest H2D bandwidth.  When the measurement cannot tell the nodes apart (within 10%) the
+    ranks are spread round-robin over the nodes instead of all landing on node 0.  Returns (previous affinity, report)."""
+    import os
+
+    prev = os.sched_getaffinity(0)
+    nodes = host_nodes()
+    report = {"nodes": len(nodes), "policy": "none"}
+    if len(nodes) < 2:
+        return prev, report
+    try:
+        bw = measure_h2d_by_node(device)
+    except Exception as e:  # measurement is best effort; the verifier does not depend on it
+        report["error"] = str(e)
+        bw = {}
+    report["h2d_gbs_by_node"] = {str(k): round(v, 2) for k, v in bw.items()}
+    if bw:
+        best = max(bw, key=bw.get)
+        worst = min(bw.values())
+        if bw[best] > 1.10 * worst:
+            node, report["policy"] = best, "measured"
+        else:
+            ids = sorted(bw)
+            node, report["policy"] = ids[(rank * len(ids)) // max(world, 1) % len(ids)], "spread"
+        cpus = nodes[node] & prev
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            report["node"] = node
+            report["cpus"] = len(cpus)
+    return prev, report

@@ -115,6 +115,120 @@ class Oracle:
         return fn(C.addressof(shape), blob.ctypes.data)
 
 
+class OracleCircuit:
+    """The oracle's OWN way in (oracle/json_reader.hpp): the reference's JSON files -> the oracle's records, no product
+    parser involved.  `proof_blob` flattens a proof in declaration order (what the product calls a blob)."""
+
+    def __init__(self, lib, common_json, vkey_json):
+        self.lib = lib
+        to_b = lambda t: t.encode() if isinstance(t, str) else t
+        cj, vj = to_b(common_json), to_b(vkey_json)
+        lib.orc_circuit_from_json.restype = C.c_void_p
+        lib.orc_circuit_from_json.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+        lib.orc_last_error.restype = C.c_char_p
+        self.h = lib.orc_circuit_from_json(cj, len(cj), vj, len(vj))
+        if not self.h:
+            raise ValueError("oracle: " + lib.orc_last_error().decode())
+        lib.orc_proof_from_json.restype = C.c_longlong
+        lib.orc_proof_from_json.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        lib.orc_vkey_words.restype = C.c_longlong
+        lib.orc_vkey_words.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        lib.orc_circuit_info.argtypes = [C.c_void_p, C.c_void_p]
+        lib.orc_testmain.restype = C.c_longlong
+        lib.orc_testmain.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        lib.orc_fri_roots.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.orc_circuit_free.argtypes = [C.c_void_p]
+        info = (C.c_int * 8)()
+        lib.orc_circuit_info(self.h, info)
+        (self.num_challenges, self.num_queries, self.num_steps, self.num_lookup_polys, self.degree_bits, self.rate_bits,
+         self.cap_height, self.num_public_inputs) = list(info)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.orc_circuit_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def vkey_words(self):
+        n = self.lib.orc_vkey_words(self.h, None, 0)
+        out = np.zeros(n, dtype=np.uint64)
+        self.lib.orc_vkey_words(self.h, out.ctypes.data, n)
+        return out
+
+    def proof_blob(self, proof_json):
+        pj = proof_json.encode() if isinstance(proof_json, str) else proof_json
+        n = self.lib.orc_proof_from_json(self.h, pj, len(pj), None, 0)
+        if n < 0:
+            raise ValueError("oracle: " + self.lib.orc_last_error().decode())
+        out = np.zeros(n, dtype=np.uint64)
+        self.lib.orc_proof_from_json(self.h, pj, len(pj), out.ctypes.data, n)
+        return out
+
+    def challenges_words(self):
+        r = self.num_challenges
+        return 3 * r + (4 * r if self.num_lookup_polys > 0 else 0) + 4 + 2 * self.num_steps + 1 + self.num_queries
+
+    def verify_batch(self, blobs, threads=8, fast=True):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint64)
+        if blobs.ndim == 1:
+            blobs = blobs.reshape(1, -1)
+        n = blobs.shape[0]
+        cw, Q, r = self.challenges_words(), self.num_queries, self.num_challenges
+        out = dict(
+            challenges=np.zeros((cw, n), dtype=np.uint64), combined=np.zeros((2 * r, n), dtype=np.uint64),
+            eqmask=np.zeros(n, dtype=np.uint8), status=np.zeros(n, dtype=np.uint32),
+            fri_status=np.zeros(n, dtype=np.uint32), qstatus=np.zeros((n, Q), dtype=np.uint32),
+            folded=np.zeros((2, n * Q), dtype=np.uint64))
+        perms = C.c_ulonglong(0)
+        fn = self.lib.orc_verify_batch_h
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]
+        fn(self.h, blobs.ctypes.data, n, threads, 1 if fast else 0, out["challenges"].ctypes.data, out["combined"].ctypes.data,
+           out["eqmask"].ctypes.data, out["status"].ctypes.data, out["fri_status"].ctypes.data, out["qstatus"].ctypes.data,
+           out["folded"].ctypes.data, C.addressof(perms))
+        out["perms"] = perms.value
+        return out
+
+    def verify_with_challenges(self, blobs, challenges_in):
+        """verifyProof against GIVEN challenges (SoA [cw][n], include/p2v.h order) -> combined, eqmask, status, qstatus, folded."""
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint64)
+        if blobs.ndim == 1:
+            blobs = blobs.reshape(1, -1)
+        n = blobs.shape[0]
+        ch = np.ascontiguousarray(challenges_in, dtype=np.uint64)
+        Q, r = self.num_queries, self.num_challenges
+        out = dict(combined=np.zeros((2 * r, n), dtype=np.uint64), eqmask=np.zeros(n, dtype=np.uint8), status=np.zeros(n, dtype=np.uint32),
+                   qstatus=np.zeros((n, Q), dtype=np.uint32), folded=np.zeros((2, n * Q), dtype=np.uint64))
+        fn = self.lib.orc_verify_with_challenges_h
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_void_p] * 6
+        fn(self.h, blobs.ctypes.data, n, ch.ctypes.data, out["combined"].ctypes.data, out["eqmask"].ctypes.data, out["status"].ctypes.data,
+           out["qstatus"].ctypes.data, out["folded"].ctypes.data)
+        return out
+
+    def fri_roots(self, blobs):
+        """Recomputed Merkle roots of every opening: SoA [(4+steps)*4][n*Q] (index p*Q+q)."""
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint64)
+        if blobs.ndim == 1:
+            blobs = blobs.reshape(1, -1)
+        n = blobs.shape[0]
+        out = np.zeros(((4 + self.num_steps) * 4, n * self.num_queries), dtype=np.uint64)
+        self.lib.orc_fri_roots(self.h, blobs.ctypes.data, n, out.ctypes.data)
+        return out
+
+    def testmain(self, proof_json):
+        pj = proof_json.encode() if isinstance(proof_json, str) else proof_json
+        buf = C.create_string_buffer(1 << 16)
+        n = self.lib.orc_testmain(self.h, pj, len(pj), buf, len(buf))
+        if n < 0:
+            raise ValueError("oracle: " + self.lib.orc_last_error().decode())
+        return buf.value.decode()
+
+
+def circuit_from_json(common_json, vkey_json):
+    return OracleCircuit(load().lib, common_json, vkey_json)
+
+
 def challenges_words_py(shape):
     r = shape.num_challenges
     return 3 * r + (4 * r if shape.num_lookup_polys > 0 else 0) + 4 + 2 * shape.num_steps + 1 + shape.num_queries
