@@ -4,9 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--proofs B] [--impl reference]
 
 Workload (BASELINE.json configs[3]/[4]): full verification (challenges + constraints + FRI) of B
-standard-recursion-shape proofs per GPU.  The batch is synthetic: the bundled accepting S12 fixture
-(tests/golden/s12_*.json) replicated B times, 3 out of 4 copies tampered in one word (the schedule
-of tests/fixtures.py).  A "step" is one pass of the hot path over that batch.
+standard-recursion-shape proofs per GPU.  The batch is synthetic: the bundled accepting `real12` fixture (the standard
+recursion configuration with an ACTIVE gate on every row; `--fixture s12` = the all-Noop variant) replicated B times,
+3 out of 4 copies tampered in one word (the schedule of tests/fixtures.py).  A "step" is one pass of the hot path
+over that batch.
 
   value : proofs/s with the AoS blobs already resident in HBM (timed: K0 stage + K4 + K5 + K6 + K7)
   e2e   : proofs/s through p2v_verify_batch with HOST (pinned) buffers: H2D of the blobs and D2H of the
@@ -15,8 +16,12 @@ of tests/fixtures.py).  A "step" is one pass of the hot path over that batch.
               against the IMAD.WIDE peak measured live on this GPU; plus achieved HBM GB/s
   cpu_baseline : the CPU oracle (C++ restatement, "port") on the host cores over a bounded sample
 
-Multi-GPU (torchrun, one rank per GPU): contiguous equal slices, no data-path collective, one NCCL
-all_gather of the accept bitmap inside the timed region; weak scaling (B proofs per GPU).
+Multi-GPU (torchrun, one rank per GPU): contiguous equal slices, no data-path collective; every step goes through the
+C export p2v_verify_batch_sharded (slice -> K0..K7 -> ncclAllGather of the accept bitmap on the verifier's stream);
+torch only launches the ranks and carries the 128-byte NCCL id.  Weak scaling (B proofs per GPU).  After the timed
+region an UNTIMED strong-scaling check (BASELINE config 5) verifies the same seeded batch sharded over the ranks and
+requires, on every rank, gathered bitmap == that rank's own single-GPU run == the oracle on a sample of every slice
+("sharded_parity").
 """
 import argparse
 import json
@@ -33,6 +38,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 IMADS_PER_PERM = 6376  # 32x32->64 multiplies per permutation (fast-partial formulation)
 METRIC = "proofs_verified_per_sec"
 UNIT = "proofs/s"
+WORKLOAD = "full verifier (challenges + constraints + FRI) on standard-recursion-shape (S12) proofs"
 
 
 def perms_per_proof(shape, lay):
@@ -115,39 +121,103 @@ def cpu_baseline(shape, lay, vkey, blobs, seconds=12.0):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path = the oracle port (no GHC in the image)."""
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (no GHC in the image).
+    Nothing of the product is loaded here: the JSON is decoded by the oracle's own reader (oracle/json_reader.hpp) and the
+    batch is the same seeded schedule prefix the GPU arm verifies (committed tamper table, tests/golden/*_tamper.json)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import numpy as np
     import fixtures
-    import plonky2_verifier_b200 as p2v  # host parser only (JSON -> blob); no GPU call is made in this arm
-
-    shape, lay, vkey, blob = fixtures.load(args.fixture)
-    cores = os.cpu_count() or 1
-    per_step = 16 * cores
-    blobs, _, _ = fixtures.tampered_batch(blob, lay, shape, per_step, seed=11)
     import oracle_lib
 
-    orc = oracle_lib.load()
+    oc = oracle_lib.circuit_from_json(fixtures.read(args.fixture, "common"), fixtures.read(args.fixture, "vkey"))
+    blob = oc.proof_blob(fixtures.read(args.fixture, "proof"))
+    cores = os.cpu_count() or 1
+    per_step = 16 * cores
+    blobs, _, _ = fixtures.tampered_batch_from_table(blob, fixtures.tamper_table(args.fixture), per_step, seed=1000)
     for _ in range(args.warmup):
-        orc.verify_batch(shape, vkey, blobs[:cores], threads=cores, fast=True)
+        oc.verify_batch(blobs[:cores], threads=cores, fast=True)
     t0 = time.time()
     for _ in range(args.steps):
-        orc.verify_batch(shape, vkey, blobs, threads=cores, fast=True)
+        res = oc.verify_batch(blobs, threads=cores, fast=True)
     dt = time.time() - t0
     value = per_step * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "full verifier (challenges + constraints + FRI) on standard-recursion-shape (S12) proofs", "proofs_per_step": per_step,
-                   "note": "CPU arm: C++ restatement of the Haskell reference on all host threads (GHC is not in the image)"},
+        "config": {"workload": WORKLOAD, "proofs_per_step": per_step, "fixture": args.fixture,
+                   "accepted_per_step": int((res["status"] == 0).sum()),
+                   "note": "CPU arm: C++ restatement of the Haskell reference on all host threads (GHC is not in the image); "
+                           "same seeded schedule prefix as the GPU arm; no product code is loaded in this arm"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": "%d proofs per step" % per_step},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+def ncu_traffic(n):
+    """dram bytes of the dominant kernel per launch, from the committed ncu --set full capture (profiles/*_traffic.json,
+    written by tools/ncu_summary.py): bytes per proof of the captured launch x the proofs of this launch."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_fri_merkle_traffic.json")))
+    if not files:
+        return None, "no committed ncu capture"
+    t = json.load(open(files[-1]))
+    per_proof = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["proofs"]
+    return per_proof * n, "%s: dram read+write = %.1f MB for %d proofs = %.1f kB per proof (ncu --set full, %s); scaled to this launch" % (
+        os.path.basename(files[-1]), (t["dram_bytes_read"] + t["dram_bytes_write"]) / 1e6, t["proofs"], per_proof / 1e3, t.get("report", "?"))
+
+
+def sharded_parity_check(p2v, sharding, dist, ctx, cir, fixtures, template, rank, world, n_par, fixture):
+    """BASELINE config 5, untimed: the SAME seeded batch on every rank, sharded with p2v_shard_bounds and verified through
+    p2v_verify_batch_sharded; on EVERY rank the gathered bitmap must equal (a) that rank's own single-GPU verification
+    of the whole batch and (b) the oracle on a sample drawn from every rank's slice.  -> (ok on all ranks, detail)."""
+    import numpy as np
+    import torch
+
+    shape, lay, vkey, blob = template
+    W = lay.blob_words
+    _, words, deltas = fixtures.tampered_batch(blob, lay, shape, min(n_par, 4096), seed=4242)
+    reps = (n_par + len(words) - 1) // len(words)
+    words_n, deltas_n = np.tile(words, reps)[:n_par].copy(), np.tile(deltas, reps)[:n_par].copy()
+    d_full = torch.empty((n_par, W), dtype=torch.int64, device="cuda")
+    cir.synth_batch(blob, n_par, words_n, deltas_n, d_full)
+    nw = (n_par + 31) // 32
+    single_bits = torch.zeros(nw, dtype=torch.int32, device="cuda")
+    single_status = torch.zeros(n_par, dtype=torch.int32, device="cuda")
+    ctx.sync()
+    cir.verifyProof(d_full, n=n_par, accept_bits=single_bits, status=single_status)
+    ctx.sync()
+    start, stop = p2v.shard_bounds(n_par, rank, world)
+    full, status_local = sharding.verify_batch_sharded(cir, d_full[start:stop], n_par, rank, world, dist)
+    torch.cuda.synchronize()
+    ok = bool(torch.equal(full[:nw], single_bits)) and bool(torch.equal(status_local, single_status[start:stop]))
+    detail = {"rank": rank, "bitmap_equal": ok}
+    # oracle on a sample of EVERY rank's slice (each rank checks all slices, so a wrong placement is seen everywhere)
+    import oracle_lib
+
+    oc = oracle_lib.circuit_from_json(fixtures.read(fixture, "common"), fixtures.read(fixture, "vkey"))
+    pick = []
+    for r in range(world):
+        a, b = p2v.shard_bounds(n_par, r, world)
+        if b > a:
+            pick += [a, (a + b) // 2 + 1, b - 1]
+    pick = sorted(set(pick))
+    sample = d_full[torch.tensor(pick, device="cuda")].cpu().numpy().view(np.uint64)
+    want = oc.verify_batch(sample, threads=min(len(pick), os.cpu_count() or 1), fast=True)["status"] == 0
+    bits = p2v.unpack_bits(full.cpu().numpy().view(np.uint32), n_par)
+    oracle_ok = bool(np.array_equal(bits[pick], want))
+    detail["oracle_sample"] = len(pick)
+    detail["oracle_equal"] = oracle_ok
+    ok = ok and oracle_ok
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+    if dist is not None:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    del d_full
+    return bool(flag.item()), detail
 
 
 def main():
@@ -158,9 +228,10 @@ def main():
     ap.add_argument("--proofs", type=int, default=100000, help="proofs per GPU per step")
     ap.add_argument("--e2e-proofs", type=int, default=0, help="proofs per GPU for the host-buffer measurement (0 = auto)")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--fixture", default="s12", choices=["s12", "real12"],
-                    help="template proof of the batch: s12 = standard recursion shape, Plonky2's own 3-group selector layout, all-Noop rows; "
-                         "real12 = same configuration with active gates on every row (4 selector groups)")
+    ap.add_argument("--fixture", default="real12", choices=["s12", "real12"],
+                    help="template proof of the batch: real12 (default) = standard recursion configuration with an active gate on every row "
+                         "(4 selector groups); s12 = same shape, Plonky2's own 3-group selector layout, all-Noop rows")
+    ap.add_argument("--parity-proofs", type=int, default=32808, help="size of the untimed same-batch sharded check at world > 1 (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="proofs per staged chunk on the host-buffer path (0 = library default)")
     args = ap.parse_args()
@@ -179,8 +250,6 @@ def main():
         raise SystemExit("bench.py needs a GPU: libp2v has no CPU fallback")
     torch.cuda.set_device(local_rank)
     from plonky2_verifier_b200 import sharding
-    # pinned staging buffers on the GPU's NUMA node (P2V_NO_NUMA_BIND=1 leaves the affinity alone: tuning aid)
-    prev_affinity = os.sched_getaffinity(0) if os.environ.get("P2V_NO_NUMA_BIND") else sharding.bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -188,11 +257,25 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
+    # Host placement of the pinned staging buffers: MEASURED, not read from sysfs (on the round-1 box every GPU reported
+    # NUMA node 0 and all eight ranks pinned their buffers there).  Ranks measure one after the other so that they do not
+    # disturb each other's probe.  P2V_NO_NUMA_BIND=1 leaves the affinity alone (tuning aid).
+    prev_affinity, placement = os.sched_getaffinity(0), {"policy": "off"}
+    if not os.environ.get("P2V_NO_NUMA_BIND"):
+        for r in range(world):
+            if r == rank:
+                prev_affinity, placement = sharding.place_on_best_node(local_rank, rank, world)
+            if dist is not None:
+                dist.barrier()
 
     shape, lay, vkey, blob = fixtures.load(args.fixture)
     ctx = p2v.Context(local_rank)
     cir = p2v.Circuit(ctx, shape, vkey)
     n = args.proofs
+    if world > 1:
+        n = max(32, n // 32 * 32)  # equal slices of the weak-scaling batch are exactly the ranks' batches
+        sharding.init_comm(ctx, dist)  # libp2v's own NCCL communicator; torch ships the 128-byte id
+    n_total = n * world
     W = lay.blob_words
     stream = torch.cuda.ExternalStream(ctx.stream)
 
@@ -204,16 +287,14 @@ def main():
     d_blobs = torch.empty((n, W), dtype=torch.int64, device="cuda")
     cir.synth_batch(blob, n, words_n, deltas_n, d_blobs)
     n_words = (n + 31) // 32
-    d_bits = torch.zeros(n_words, dtype=torch.int32, device="cuda")
+    words_full = p2v.shard_slice_len(n_total, world) // 32 * world
+    d_bits = torch.zeros(words_full, dtype=torch.int32, device="cuda")  # world == 1: the bitmap; else the GATHERED bitmap
     d_status = torch.zeros(n, dtype=torch.int32, device="cuda")
-    gathered = torch.zeros(n_words * world, dtype=torch.int32, device="cuda") if world > 1 else None
     ctx.sync()
 
     def step_device():
-        cir.verifyProof(d_blobs, n=n, accept_bits=d_bits, status=d_status)
-        if dist is not None:
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(gathered, d_bits)
+        # one C-ABI call per step: world == 1 -> p2v_verify_batch, else p2v_verify_batch_sharded (verify + ncclAllGather)
+        cir.verifyProofSharded(d_blobs, n_total, rank, world, accept_bits_full=d_bits, status=d_status)
 
     def barrier():
         ctx.sync()
@@ -256,34 +337,43 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = n * world / (ms_per_step * 1e-3)
+    value = n_total / (ms_per_step * 1e-3)
 
-    # ---- correctness of what was timed: verdicts of a prefix vs the oracle (rank 0, outside the timing) ----
+    # ---- correctness of what was timed (outside the timing) ----
     status_host = d_status.cpu().numpy().view(np.uint32)
-    accept_host = p2v.unpack_bits(d_bits.cpu().numpy().view(np.uint32), n)
-    assert np.array_equal(accept_host, status_host == 0)
+    bits_all = d_bits.cpu().numpy().view(np.uint32)
+    accept_host = p2v.unpack_bits(bits_all[rank * n_words:(rank + 1) * n_words], n)
+    assert np.array_equal(accept_host, status_host == 0), "this rank's slice of the gathered bitmap differs from its status words"
     if dist is not None:
-        g = gathered.cpu().numpy().view(np.uint32).reshape(world, n_words)
-        assert np.array_equal(g[rank], d_bits.cpu().numpy().view(np.uint32)), "allgather returned a different bitmap"
+        # every rank's slice must sit at words [k*W, (k+1)*W) of EVERY rank's bitmap: compare with a torch all_gather of the
+        # bits recomputed from the status words (a second, independent route; untimed)
+        mine = torch.from_numpy(sharding.pack_bits(status_host == 0).view(np.int32)).cuda()
+        check = torch.empty(n_words * world, dtype=torch.int32, device="cuda")
+        dist.all_gather_into_tensor(check, mine)
+        assert torch.equal(check, d_bits), "p2v_verify_batch_sharded gathered a different bitmap than torch.distributed"
 
     # ---- e2e: host buffers through the C ABI ----
     import psutil
 
-    avail = psutil.virtual_memory().available
+    avail = psutil.virtual_memory().available // max(world, 1)
     n_e2e = args.e2e_proofs or n
     while n_e2e * W * 8 * 3 > avail and n_e2e > 1024:
         n_e2e //= 2
+    if world > 1:
+        n_e2e = max(32, n_e2e // 32 * 32)
     h_blobs_t = torch.empty((n_e2e, W), dtype=torch.int64, pin_memory=True)
     h_blobs = h_blobs_t.numpy().view(np.uint64)
     src = d_blobs[:n_e2e].cpu().numpy().view(np.uint64)
     h_blobs[:] = src
     del src
-    h_bits_t = torch.zeros((n_e2e + 31) // 32, dtype=torch.int32, pin_memory=True)
+    e2e_words_full = p2v.shard_slice_len(n_e2e * world, world) // 32 * world
+    h_bits_t = torch.zeros(e2e_words_full, dtype=torch.int32, pin_memory=True)
     h_status_t = torch.zeros(n_e2e, dtype=torch.int32, pin_memory=True)
     h_bits, h_status = h_bits_t.numpy().view(np.uint32), h_status_t.numpy().view(np.uint32)
 
     def step_host():
-        cir.verifyProof(h_blobs, n=n_e2e, accept_bits=h_bits, status=h_status)  # synchronous: outputs are host buffers
+        # synchronous: outputs are host buffers (H2D of the blobs, D2H of the gathered bitmap + status inside the call)
+        cir.verifyProofSharded(h_blobs, n_e2e * world, rank, world, accept_bits_full=h_bits, status=h_status)
 
     if args.e2e_chunk:
         ctx.set_chunk(args.e2e_chunk)
@@ -306,16 +396,38 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = n_e2e * world * e2e_steps / float(te.item())
     assert np.array_equal(h_status, status_host[:n_e2e]), "host-buffer path and device-resident path disagree"
-    # raw pinned-host -> device copy bandwidth of this box (what bounds the end-to-end path)
+    # raw pinned-host -> device copy bandwidth: alone (ranks take turns) and with every rank copying at once
     probe_n = min(n_e2e, 16384)
     d_probe = torch.empty((probe_n, W), dtype=torch.int64, device="cuda")
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        d_probe.copy_(h_blobs_t[:probe_n], non_blocking=True)
-    torch.cuda.synchronize()
-    h2d_gbs = 3 * probe_n * W * 8 / (time.perf_counter() - t0) / 1e9
+
+    def probe():
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            d_probe.copy_(h_blobs_t[:probe_n], non_blocking=True)
+        torch.cuda.synchronize()
+        return 3 * probe_n * W * 8 / (time.perf_counter() - t0) / 1e9
+
+    h2d_alone = 0.0
+    for r in range(world):
+        if r == rank:
+            h2d_alone = probe()
+        if dist is not None:
+            dist.barrier()
+    h2d_together = probe() if world > 1 else h2d_alone
     del d_probe
+    stats = torch.tensor([h2d_alone, h2d_together, float(placement.get("node", -1))], dtype=torch.float64, device="cuda")
+    all_stats = [stats.clone() for _ in range(world)]
+    if dist is not None:
+        dist.all_gather(all_stats, stats)
+    all_stats = [[float(x) for x in s_.cpu()] for s_ in all_stats]
+
+    # ---- BASELINE config 5: same batch sharded over the ranks, bitmap identical to the 1-GPU run (untimed) ----
+    parity = None
+    if world > 1 and args.parity_proofs > 0:
+        ok, detail = sharded_parity_check(p2v, sharding, dist, ctx, cir, fixtures, (shape, lay, vkey, blob), rank, world, args.parity_proofs, args.fixture)
+        parity = {"sharded_parity": "ok" if ok else "FAILED", "sharded_n": args.parity_proofs, "rank0": detail}
+        assert ok, "sharded verification disagrees with the single-GPU run / the oracle: %r" % (detail,)
 
     if rank != 0:
         if dist is not None:
@@ -336,6 +448,7 @@ def main():
     hbm_src = "measured" if "hbm_gbs" in peaks else "fallback"
     algo_bytes = n * W * 8 * 2 + n * W * 8  # K0 reads AoS + writes SoA, later kernels read the planes once
     hbm_achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(n)
 
     cpu = None
     os.sched_setaffinity(0, prev_affinity)  # the CPU baseline gets every host core again
@@ -345,26 +458,34 @@ def main():
         assert np.array_equal(cpu_res["status"], status_host[:sample]), "GPU verdicts differ from the CPU oracle"
 
     hist = {}
-    for s in status_host:
-        hist[int(s) & 0xFF] = hist.get(int(s) & 0xFF, 0) + 1
+    for s_ in status_host:
+        hist[int(s_) & 0xFF] = hist.get(int(s_) & 0xFF, 0) + 1
+    alone = sorted(x[0] for x in all_stats)
+    together = sorted(x[1] for x in all_stats)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": "full verifier (challenges + constraints + FRI) on standard-recursion-shape (S12) proofs",
+        "config": {"workload": WORKLOAD, "fixture": args.fixture,
                    "proofs_per_gpu": n, "blob_bytes": W * 8, "queries": shape.num_queries, "perms_per_proof": 114 + shape.num_queries * ppq,
                    "l2": "inputs (%.1f GB per step) are far larger than L2" % (n * W * 8 / 1e9),
                    "batch": "bundled %s fixture x %d, 3 of 4 copies tampered in one word" % (args.fixture, n),
-                   "verdict_histogram": hist, "host_numa": "process bound to the GPU's NUMA node (%d cpus) for the pinned staging buffers" % len(os.sched_getaffinity(0)), "pipeline": "4 lanes (stream + workspace); chunks of 3 GiB (device-resident input) / 0.5 GiB (host input); K0/K4/K5 of the next chunks overlap K6 of the current one", "multi_gpu": "contiguous slices + NCCL all_gather of the accept bitmap" if world > 1 else "single GPU"},
+                   "verdict_histogram": hist,
+                   "host_placement": placement,
+                   "pipeline": "4 lanes (stream + workspace); chunks of 3 GiB (device-resident input) / 0.5 GiB (host input); K0/K4/K5 of the next chunks overlap K6 of the current one",
+                   "multi_gpu": ("contiguous slices, one C-ABI call per step: p2v_verify_batch_sharded = verify + ncclAllGather of the accept bitmap "
+                                 "(libp2v's own communicator, NCCL %s)" % (ctx.nccl_info()[2],)) if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * W * 8, "d2h_bytes_per_step": int(h_bits.nbytes + h_status.nbytes),
-                "proofs_per_gpu": n_e2e, "h2d_copy_gbs_measured": h2d_gbs,
-                "h2d_bound_proofs_per_s": h2d_gbs * 1e9 / (W * 8) * world},
+                "proofs_per_gpu": n_e2e, "h2d_copy_gbs_measured": alone[len(alone) // 2],
+                "h2d_copy_gbs_per_rank_alone": {"min": alone[0], "median": alone[len(alone) // 2], "max": alone[-1]},
+                "h2d_copy_gbs_per_rank_all_ranks_copying": {"min": together[0], "median": together[len(together) // 2], "max": together[-1]},
+                "host_node_per_rank": [int(x[2]) for x in all_stats],
+                "h2d_bound_proofs_per_s": sum(together) * 1e9 / (W * 8)},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "int_pipe", "kernel": "k_fri_merkle", "achieved": achieved / 1e9, "peak": imad_peak / 1e9, "unit": "GIMAD/s",
-                     "frac": achieved / imad_peak, "traffic": 124900.0 * n, "traffic_unit": "bytes per launch",
-                     "traffic_source": "ncu --set full (profiles/r01_k_fri_merkle_ncu.md): dram read+write = 383.7 MB for 3072 proofs = "
-                                       "124.9 kB per proof, 1.04x the algorithmic 28 x 536 x 8 B; scaled to this launch",
+                     "frac": achieved / imad_peak, "traffic": traffic, "traffic_unit": "bytes per launch",
+                     "traffic_source": traffic_src,
                      "algorithmic_bytes": float(shape.num_queries * lay.query_words * 8 * n),
                      "perms_per_s": perms_per_s, "kernel_ms": fri_ms,
                      "peak_source": "IMAD.WIDE.U32 issue rate measured live on this GPU (p2v_int_pipe_peak mode 0: 32/clk/SM, "
@@ -375,6 +496,8 @@ def main():
         "kernel_ms": sec_ms, "kernel_ms_note": "serial single-chunk pass outside the timed region",
         "cpu_baseline": cpu,
     }
+    if parity:
+        line.update(parity)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -356,7 +356,9 @@ int p2v_debug_field_op(p2v_ctx *ctx, int op, const uint64_t *a, const uint64_t *
  * mode 0: LOP3 + IMAD.WIDE.U32, 1: 2 LOP3 + IMAD.WIDE.U32, 2: LOP3 + IMAD (32-bit), 3: LOP3 + IADD3,
  * 4: 2 IMAD.WIDE.U32 + LOP3, 5: 2 IMAD (32-bit), 6: 2 LOP3, 7: IMAD.WIDE.U32 alone, 8: 2 SHF, 9: IADD3 + IADD3.X,
  * 10: DFMA, 11: DFMA + LOP3 + IMAD, 12: DADD, 13: I2F.F64.U32 + LOP3, 14: mode 13 next to a DFMA chain,
- * 15: mode 13 next to an IMAD.WIDE.U32 chain.
+ * 15: mode 13 next to an IMAD.WIDE.U32 chain.  16..23: operand-bandwidth probes with three distinct register sources per
+ * instruction (hash_kernels.cuh k_rf_probe): 16 IADD3, 17 LOP3, 18 DFMA (3 registers), 19 DFMA (2 registers + immediate),
+ * 20 = 18 + 16, 21 = 19 + 16, 22 IMAD.WIDE with a 64-bit accumulator, 23 = 22 + 19 + 16.
  * *ops_per_s = groups per second summed over all threads. */
 int p2v_int_pipe_peak(p2v_ctx *ctx, int mode, double *ops_per_s);
 /* Device time (ms) of a section of the most recent batch call (last chunk): "stage" (K0), "challenges" (K4),

@@ -287,7 +287,7 @@ int p2v_debug_field_op(p2v_ctx *ctx, int op, const uint64_t *a, const uint64_t *
 
 // ---- measurement helper -------------------------------------------------------------------
 int p2v_int_pipe_peak(p2v_ctx *ctx, int mode, double *ops_per_s) {
-  if (!ctx || !ops_per_s || mode < 0 || mode > 15) return p2v_fail(ctx, P2V_E_INVALID, "p2v_int_pipe_peak: bad argument");
+  if (!ctx || !ops_per_s || mode < 0 || mode > 23) return p2v_fail(ctx, P2V_E_INVALID, "p2v_int_pipe_peak: bad argument");
   P2V_CUDA(ctx, cudaSetDevice(ctx->device));
   u64 *d = nullptr;
   P2V_CUDA(ctx, cudaMalloc(&d, 8));
@@ -312,7 +312,15 @@ int p2v_int_pipe_peak(p2v_ctx *ctx, int mode, double *ops_per_s) {
       case 12: P2V_LAUNCH(ctx, k_int_pipe<12>, grid, block, 0, d, iters, 12345u); break;
       case 13: P2V_LAUNCH(ctx, k_int_pipe<13>, grid, block, 0, d, iters, 12345u); break;
       case 14: P2V_LAUNCH(ctx, k_int_pipe<14>, grid, block, 0, d, iters, 12345u); break;
-      default: P2V_LAUNCH(ctx, k_int_pipe<15>, grid, block, 0, d, iters, 12345u); break;
+      case 15: P2V_LAUNCH(ctx, k_int_pipe<15>, grid, block, 0, d, iters, 12345u); break;
+      case 16: P2V_LAUNCH(ctx, k_rf_probe<16>, grid, block, 0, d, iters, 12345u); break;
+      case 17: P2V_LAUNCH(ctx, k_rf_probe<17>, grid, block, 0, d, iters, 12345u); break;
+      case 18: P2V_LAUNCH(ctx, k_rf_probe<18>, grid, block, 0, d, iters, 12345u); break;
+      case 19: P2V_LAUNCH(ctx, k_rf_probe<19>, grid, block, 0, d, iters, 12345u); break;
+      case 20: P2V_LAUNCH(ctx, k_rf_probe<20>, grid, block, 0, d, iters, 12345u); break;
+      case 21: P2V_LAUNCH(ctx, k_rf_probe<21>, grid, block, 0, d, iters, 12345u); break;
+      case 22: P2V_LAUNCH(ctx, k_rf_probe<22>, grid, block, 0, d, iters, 12345u); break;
+      default: P2V_LAUNCH(ctx, k_rf_probe<23>, grid, block, 0, d, iters, 12345u); break;
     }
     P2V_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     P2V_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));

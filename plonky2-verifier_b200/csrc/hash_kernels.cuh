@@ -246,6 +246,44 @@ __global__ void __launch_bounds__(256) k_int_pipe(u64 *out, u32 iters, u32 seed)
   if (acc == 0x1234567812345678ULL) out[0] = acc;  // keep the chains alive
 }
 
+// Register-file / operand-bandwidth probe (p2v_int_pipe_peak modes 16..23): the same pipes as k_int_pipe but with THREE
+// distinct register sources per instruction, spread over 24 live registers, the way real code reads operands.
+//   16: IADD3 a = a + b + c     17: LOP3 a = f(a, b, c)     18: DFMA d = d * e + f (three 64-bit registers)
+//   19: DFMA d = e * imm + d    20: 18 + 16 interleaved      21: 19 + 16 interleaved
+//   22: IMAD.WIDE acc = x * y + acc (two 32-bit + one 64-bit register)   23: 22 + 19 + 16 interleaved
+template <int MODE>
+__global__ void __launch_bounds__(256) k_rf_probe(u64 *out, u32 iters, u32 seed) {
+  u32 x = threadIdx.x * 2654435761u + seed;
+  u32 a[8], b[8], c[8];
+  double d[8], e[8], f[8];
+  u64 w[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a[i] = x * (i + 3); b[i] = x * (i + 11) + 1; c[i] = x * (i + 19) + 2;
+    d[i] = 1.0 + 1e-9 * (double)(a[i] & 0xffff); e[i] = 1.0 + 1e-12 * (double)(b[i] & 0xffff); f[i] = 1e-9 * (double)(c[i] & 0xffff);
+    w[i] = (u64)a[i] * b[i];
+  }
+#pragma unroll 1
+  for (u32 it = 0; it < iters; it++) {
+#pragma unroll
+    for (int rep = 0; rep < 8; rep++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int j = (i + 3) & 7, k = (i + 5) & 7;
+        if (MODE == 16 || MODE == 20 || MODE == 21 || MODE == 23) asm volatile("{.reg .u32 t; add.u32 t,%1,%2; add.u32 %0,%0,t;}" : "+r"(a[i]) : "r"(b[j]), "r"(c[k]));
+        if (MODE == 17) asm volatile("lop3.b32 %0,%0,%1,%2,0x96;" : "+r"(a[i]) : "r"(b[j]), "r"(c[k]));
+        if (MODE == 18 || MODE == 20) asm volatile("fma.rn.f64 %0,%0,%1,%2;" : "+d"(d[i]) : "d"(e[j]), "d"(f[k]));
+        if (MODE == 19 || MODE == 21 || MODE == 23) asm volatile("fma.rn.f64 %0,%1,0d4000000000000000,%0;" : "+d"(d[i]) : "d"(e[j]));
+        if (MODE == 22 || MODE == 23) asm volatile("{.reg .u32 lo,hi; mov.b64 {lo,hi},%1; mad.wide.u32 %0,lo,%2,%0;}" : "+l"(w[i]) : "l"(w[j]), "r"(c[k]));
+      }
+    }
+  }
+  u64 acc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc += a[i] + (u64)__double_as_longlong(d[i]) + w[i];
+  if (acc == 0x1234567812345678ULL) out[0] = acc;
+}
+
 // Test hook (p2v_debug_field_op): the device field routines of gl.cuh one by one on caller-chosen operands, so that the
 // lazy-representation edge values (0, 1, p-1, p, p+1, 2^64-1, 2^32+-1) reach every routine directly and `inv 0 = 0`
 // (Algebra/Goldilocks.hs:155, GoldilocksExt.hs:75-80) is tested on the GPU.  Outputs are canonical.

@@ -355,6 +355,8 @@ class JsonDoc {
     } else if (c == '-' || (c >= '0' && c <= '9')) {
       const char *s = p_;
       if (*p_ == '-') p_++;
+      // JSON grammar (and aeson): no leading zeros — "0" is a number, "007" is not
+      if (end_ - p_ >= 2 && p_[0] == '0' && (unsigned)(p_[1] - '0') < 10) throw JsonError("number with a leading zero");
       while (end_ - p_ >= 8 && eightDigits(p_)) p_ += 8;
       while (p_ < end_ && (unsigned)(*p_ - '0') < 10) p_++;
       while (p_ < end_ && ((*p_ >= '0' && *p_ <= '9') || *p_ == '.' || *p_ == 'e' || *p_ == 'E' || *p_ == '+' || *p_ == '-')) p_++;

@@ -263,8 +263,60 @@ void parseGateString(const char *s, size_t n, p2v_gate &g, uint64_t *weights) {
   g.kind = P2V_GATE_UNKNOWN;  // UnknownGate <$> many anyToken
 }
 
+// every integer of a shape that enters an offset, a loop bound or a shift, range-checked BEFORE it is used (a shape may
+// come from p2v_parse_common or straight from a caller)
+int validateShape(const p2v_shape &s) {
+  auto in = [](long long v, long long lo, long long hi) { return v >= lo && v <= hi; };
+  if (!in(s.num_wires, 1, 1 << 16) || !in(s.num_routed_wires, 1, P2V_MAX_ROUTED) || s.num_routed_wires > s.num_wires)
+    return fail(P2V_E_UNSUPPORTED, "num_wires / num_routed_wires out of range");
+  if (!in(s.num_gate_constants, 0, 1 << 12) || !in(s.num_constants, 0, 1 << 12)) return fail(P2V_E_UNSUPPORTED, "number of constants out of range");
+  if (!in(s.num_challenges, 1, 8)) return fail(P2V_E_UNSUPPORTED, "num_challenges out of range");
+  if (!in(s.degree_bits, 0, 31) || !in(s.rate_bits, 0, 31) || s.degree_bits + s.rate_bits > 31) return fail(P2V_E_UNSUPPORTED, "FRI parameters out of range");
+  if (!in(s.cap_height, 0, 24) || s.cap_height > s.degree_bits + s.rate_bits) return fail(P2V_E_UNSUPPORTED, "cap_height out of range");
+  if (!in(s.pow_bits, 0, 64) || !in(s.num_queries, 1, 1 << 12)) return fail(P2V_E_UNSUPPORTED, "proof_of_work_bits / num_query_rounds out of range");
+  if (!in(s.num_steps, 0, P2V_MAX_STEPS)) return fail(P2V_E_UNSUPPORTED, "too many FRI reduction steps");
+  int total = 0;
+  for (int i = 0; i < s.num_steps; i++) {
+    if (!in(s.step_arity_bits[i], 1, 8)) return fail(P2V_E_UNSUPPORTED, "FRI arity bits out of range");
+    total += s.step_arity_bits[i];
+  }
+  if (total > s.degree_bits || s.final_poly_len != (1 << (s.degree_bits - total))) return fail(P2V_E_UNSUPPORTED, "reduction strategy and final polynomial length disagree");
+  if (!in(s.quotient_degree_factor, 1, 64) || !in(s.num_public_inputs, 0, 1 << 20) || !in(s.num_partial_products, 0, 1 << 12))
+    return fail(P2V_E_UNSUPPORTED, "circuit parameters out of range");
+  if (!in(s.num_lookup_polys, 0, 1 << 10) || !in(s.num_lookup_selectors, 0, 4 + P2V_MAX_LUTS) || !in(s.num_luts, 0, P2V_MAX_LUTS))
+    return fail(P2V_E_UNSUPPORTED, "lookup parameters out of range");
+  // Plonk/Lookups.hs:57: lookup_deg = quotient_degree_factor - 1 chunks the looking columns; 0 would divide by zero
+  if (s.num_luts > 0 && s.quotient_degree_factor < 2) return fail(P2V_E_UNSUPPORTED, "lookup tables need quotient_degree_factor >= 2");
+  if (!in(s.num_gates, 0, P2V_MAX_GATES) || !in(s.num_groups, 0, P2V_MAX_GROUPS) || !in(s.num_weights, 0, P2V_MAX_WEIGHTS))
+    return fail(P2V_E_UNSUPPORTED, "gate list out of range");
+  for (int g = 0; g < s.num_groups; g++)
+    if (!in(s.group_start[g], 0, s.num_gates) || !in(s.group_end[g], s.group_start[g], s.num_gates)) return fail(P2V_E_SHAPE, "selector group range out of bounds");
+  for (int k = 0; k < s.num_gates; k++) {
+    const p2v_gate &g = s.gates[k];
+    if (!in(g.group, 0, s.num_groups - 1)) return fail(P2V_E_SHAPE, "selector index out of range ((!!) in Gate/Selector.hs:85)");
+    if (!in(g.p0, 0, 1 << 16) || !in(g.p1, 0, 1 << 30) || !in(g.p2, 0, 1 << 16)) return fail(P2V_E_UNSUPPORTED, "gate parameter out of range");
+    if (g.weights_len < 0 || g.weights_off < 0 || g.weights_off + g.weights_len > s.num_weights) return fail(P2V_E_SHAPE, "gate weights out of bounds");
+  }
+  for (int l = 0; l < s.num_luts; l++)
+    if (s.lut_off[l] < 0 || s.lut_off[l + 1] < s.lut_off[l]) return fail(P2V_E_SHAPE, "lookup table offsets are not increasing");
+  return P2V_OK;
+}
+
 int layoutImpl(const p2v_shape &s, p2v_layout &L) {
   memset(&L, 0, sizeof L);
+  int rc = validateShape(s);
+  if (rc != P2V_OK) return rc;
+  {  // sizes in 64 bits first: the 32-bit offsets below are only computed when everything fits
+    long long capw = 4LL << s.cap_height, r = s.num_challenges;
+    long long proof = 3 * capw + 2LL * (s.num_constants + s.num_routed_wires + s.num_wires + 2 * r + r * s.num_partial_products +
+                                         r * s.quotient_degree_factor + 2 * r * s.num_lookup_polys) +
+                      s.num_steps * capw + 2LL * s.final_poly_len + 1 + s.num_public_inputs;
+    long long plen = s.degree_bits + s.rate_bits - s.cap_height;
+    long long query = (long long)s.num_constants + s.num_routed_wires + s.num_wires + r * (1 + s.num_partial_products + s.num_lookup_polys) +
+                      r * s.quotient_degree_factor + 16 * plen;
+    for (int st = 0; st < s.num_steps; st++) query += (2LL << s.step_arity_bits[st]) + 4 * plen;
+    if (proof + (long long)s.num_queries * query > 0x7fffffffLL) return fail(P2V_E_UNSUPPORTED, "proof blob too large");
+  }
   int r = s.num_challenges;
   int cap = 4 << s.cap_height;
   L.cap_words = cap;
@@ -374,6 +426,7 @@ struct FastScan {
     while (p < end && (unsigned)(*p - '0') < 10) p++;
     size_t nd = (size_t)(p - t);
     if (nd == 0 || nd > 38) return ok = false;
+    if (nd > 1 && t[0] == '0') return ok = false;  // leading zeros are not JSON (aeson rejects them): let the tape reader decide
     if (p < end && (*p == '.' || *p == 'e' || *p == 'E' || *p == '-' || *p == '+')) return ok = false;
     const uint64_t P = 0xFFFFFFFF00000001ULL;
     size_t n1 = nd > 19 ? nd - 19 : 0, i = 0;
@@ -509,10 +562,16 @@ int p2v_parse_common(const char *json, size_t len, p2v_shape *out) {
     JValue root = doc.root();
     const JValue &cfg = root.at("config");
     p2v_shape &s = *out;
-    s.num_wires = (int)cfg.at("num_wires").integer();
-    s.num_routed_wires = (int)cfg.at("num_routed_wires").integer();
-    s.num_gate_constants = (int)cfg.at("num_constants").integer();
-    s.num_challenges = (int)cfg.at("num_challenges").integer();
+    // long long -> int32 with a range check (an out-of-range value must not wrap into a plausible one)
+    auto i32 = [](const JValue &v, const char *what) {
+      long long x = v.integer();
+      if (x < -(1LL << 30) || x > (1LL << 30)) throw JsonError(std::string(what) + ": integer out of range");
+      return (int)x;
+    };
+    s.num_wires = i32(cfg.at("num_wires"), "num_wires");
+    s.num_routed_wires = i32(cfg.at("num_routed_wires"), "num_routed_wires");
+    s.num_gate_constants = i32(cfg.at("num_constants"), "config.num_constants");
+    s.num_challenges = i32(cfg.at("num_challenges"), "num_challenges");
     // the remaining CircuitConfig fields are required by the generic aeson instance (Types.hs:87)
     cfg.at("use_base_arithmetic_gate").boolean();
     cfg.at("security_bits").integer();
@@ -523,10 +582,10 @@ int p2v_parse_common(const char *json, size_t len, p2v_shape *out) {
     const JValue &fp = root.at("fri_params");
     const JValue &fc2 = fp.at("config");
     auto friInts = [&](const JValue &c, int v[4]) {
-      v[0] = (int)c.at("rate_bits").integer();
-      v[1] = (int)c.at("cap_height").integer();
-      v[2] = (int)c.at("proof_of_work_bits").integer();
-      v[3] = (int)c.at("num_query_rounds").integer();
+      v[0] = i32(c.at("rate_bits"), "rate_bits");
+      v[1] = i32(c.at("cap_height"), "cap_height");
+      v[2] = i32(c.at("proof_of_work_bits"), "proof_of_work_bits");
+      v[3] = i32(c.at("num_query_rounds"), "num_query_rounds");
     };
     int a[4], b[4];
     friInts(fc, a);
@@ -539,7 +598,7 @@ int p2v_parse_common(const char *json, size_t len, p2v_shape *out) {
     s.rate_bits = a[0]; s.cap_height = a[1]; s.pow_bits = a[2]; s.num_queries = a[3];
     bool hiding = fp.at("hiding").boolean();
     if (zk || hiding) return fail(P2V_E_UNSUPPORTED, "zero-knowledge / hiding (salted leaves) is not supported (reference README.md:34)");
-    s.degree_bits = (int)fp.at("degree_bits").integer();
+    s.degree_bits = i32(fp.at("degree_bits"), "degree_bits");
     fp.at("reduction_arity_bits").list();
     if (s.degree_bits < 0 || s.degree_bits + s.rate_bits > 31 || s.rate_bits < 0 || s.cap_height < 0 || s.pow_bits < 0 || s.pow_bits > 64)
       return fail(P2V_E_UNSUPPORTED, "FRI parameters out of range");
@@ -559,11 +618,11 @@ int p2v_parse_common(const char *json, size_t len, p2v_shape *out) {
     if (key == "ConstantArityBits") {
       const auto &ab = sval.list();
       if (ab.size() != 2) throw JsonError("ConstantArityBits: expecting [arity_bits, final_poly_bits]");
-      int arity = (int)ab[0].integer(), final_bits = (int)ab[1].integer();
+      int arity = i32(ab[0], "arity_bits"), final_bits = i32(ab[1], "final_poly_bits");
       if (arity < 1) throw JsonError("ConstantArityBits: arity_bits < 1 does not terminate");
       for (int logn = s.degree_bits; logn > final_bits; logn -= arity) addStep(arity);
     } else if (key == "Fixed") {
-      for (auto &x : sval.list()) addStep((int)x.integer());
+      for (auto &x : sval.list()) addStep(i32(x, "Fixed arity"));
     } else if (key == "MinSize") {
       return fail(P2V_E_UNSUPPORTED, "reduction strategy not implemented (Plonk/FRI.hs:342)");
     } else {
@@ -571,13 +630,13 @@ int p2v_parse_common(const char *json, size_t len, p2v_shape *out) {
     }
     if (total > s.degree_bits) return fail(P2V_E_UNSUPPORTED, "reduction strategy folds below degree 1");
     s.final_poly_len = 1 << (s.degree_bits - total);
-    s.quotient_degree_factor = (int)root.at("quotient_degree_factor").integer();
+    s.quotient_degree_factor = i32(root.at("quotient_degree_factor"), "quotient_degree_factor");
     root.at("num_gate_constraints").integer();
-    s.num_constants = (int)root.at("num_constants").integer();
-    s.num_public_inputs = (int)root.at("num_public_inputs").integer();
-    s.num_partial_products = (int)root.at("num_partial_products").integer();
-    s.num_lookup_polys = (int)root.at("num_lookup_polys").integer();
-    s.num_lookup_selectors = (int)root.at("num_lookup_selectors").integer();
+    s.num_constants = i32(root.at("num_constants"), "num_constants");
+    s.num_public_inputs = i32(root.at("num_public_inputs"), "num_public_inputs");
+    s.num_partial_products = i32(root.at("num_partial_products"), "num_partial_products");
+    s.num_lookup_polys = i32(root.at("num_lookup_polys"), "num_lookup_polys");
+    s.num_lookup_selectors = i32(root.at("num_lookup_selectors"), "num_lookup_selectors");
     const auto &kis = root.at("k_is").list();
     if ((int)kis.size() > P2V_MAX_ROUTED || s.num_routed_wires > P2V_MAX_ROUTED) return fail(P2V_E_UNSUPPORTED, "more than P2V_MAX_ROUTED routed wires");
     // Vanishing.hs:107 zips k_is with the wires: extra k_is are ignored, missing ones shorten the product
@@ -594,15 +653,15 @@ int p2v_parse_common(const char *json, size_t len, p2v_shape *out) {
     s.num_gates = (int)gates.size();
     s.num_groups = (int)groups.size();
     for (size_t g = 0; g < groups.size(); g++) {
-      s.group_start[g] = (int)groups[g].at("start").integer();
-      s.group_end[g] = (int)groups[g].at("end").integer();
+      s.group_start[g] = i32(groups[g].at("start"), "group start");
+      s.group_end[g] = i32(groups[g].at("end"), "group end");
     }
     for (size_t k = 0; k < gates.size(); k++) {
       uint64_t w[P2V_MAX_WEIGHTS];
       p2v_gate g;
       const std::string &txt = gates[k].str();
       parseGateString(txt.data(), txt.size(), g, w);
-      g.group = (int)sidx[k].integer();
+      g.group = i32(sidx[k], "selector index");
       if (g.group < 0 || g.group >= s.num_groups) return fail(P2V_E_SHAPE, "selector index out of range ((!!) in Gate/Selector.hs:85)");
       if (g.weights_len) {
         if (s.num_weights + g.weights_len > P2V_MAX_WEIGHTS) return fail(P2V_E_UNSUPPORTED, "too many barycentric weights");
@@ -643,9 +702,12 @@ int p2v_parse_common(const char *json, size_t len, p2v_shape *out) {
       p2v_shape_free(out);
       return fail(P2V_E_SHAPE, "getSelectorConfig: fatal: constant columns tally does not add up!");
     }
-    if (s.num_challenges < 1 || s.num_challenges > 8 || s.quotient_degree_factor < 1 || s.num_wires < s.num_routed_wires) {
-      p2v_shape_free(out);
-      return fail(P2V_E_UNSUPPORTED, "circuit parameters out of range");
+    {
+      int vrc = validateShape(s);
+      if (vrc != P2V_OK) {
+        p2v_shape_free(out);
+        return vrc;
+      }
     }
   } catch (const std::exception &e) {
     delete[] luts;

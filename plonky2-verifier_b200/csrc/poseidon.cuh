@@ -71,7 +71,15 @@ static __constant__ PoseidonRcLimbs c_rc3 = poseidon_make_rc_limbs();
   { 17u, 15u, 41u, 16u, 2u, 28u, 13u, 13u, 39u, 18u, 34u, 20u }
 
 // x^7 with 2 squarings + 2 multiplications (sbox1, Hash/Poseidon.hs:79-80)
+#ifndef P2V_WHATIF
+#define P2V_WHATIF 0 /* analysis builds only (WRONG results, tools/whatif.sh): marginal cost of a component of the permutation */
+#endif
 __device__ __forceinline__ u64 poseidon_sbox(u64 x) {
+#if P2V_WHATIF == 1
+  return gl_mul(x, x);  // one mulmod instead of four
+#elif P2V_WHATIF == 2
+  return x + 1;         // no s-box at all
+#endif
   u64 x2 = gl_mul(x, x);
   u64 x3 = gl_mul(x, x2);
   u64 x4 = gl_mul(x2, x2);
@@ -429,8 +437,12 @@ __device__ __forceinline__ void poseidon_crt64_col(double (&SL)[6], double (&DL)
   constexpr double qc = (double)(d < 6 ? Qc[d] : -Qc[d - 6]);
   SL[I] = fma(xpL, pc, SL[I]);
   DL[I] = fma(xmL, qc, DL[I]);
+#if P2V_WHATIF == 4
+  if (I == 0) { SH[I] = fma(xpH, pc, SH[I]); DH[I] = fma(xmH, qc, DH[I]); }  // 1/6 of the high-part multiply-adds
+#else
   SH[I] = fma(xpH, pc, SH[I]);
   DH[I] = fma(xmH, qc, DH[I]);
+#endif
   if constexpr (I + 1 < 6) poseidon_crt64_col<J, I + 1>(SL, DL, SH, DH, xpL, xmL, xpH, xmH);
 }
 // biased butterfly of the pair (x_J, x_{J+6}) and its accumulation
@@ -452,6 +464,9 @@ __device__ __forceinline__ void poseidon_crt64_pair(u64 xj, u64 xk, double (&SL)
 }
 __device__ __forceinline__ u64 poseidon_crt64_fold(double TL, double TH) {
   u32 Ll = (u32)__double2loint(TL), RL = (u32)__double2hiint(TL), Hl = (u32)__double2loint(TH), RH = (u32)__double2hiint(TH);
+#if P2V_WHATIF == 3
+  return ((u64)(RL + Hl + RH) << 32) | Ll;  // no modular fold (2 adds instead of 8 instructions)
+#endif
   u32 r0, r1;
   asm("{\n\t.reg .u32 w2,c;\n\t"
       "add.cc.u32 %1,%3,%4;\n\taddc.u32 w2,%5,0;\n\t"

@@ -316,14 +316,30 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   if ((rc = o_bits.init(ctx, out.accept_bits, (n + 31) / 32 * 4))) return rc;
   if ((rc = o_qs.init(ctx, out.qstatus, n * d.Q * 4))) return rc;
   if ((rc = o_folded.init(ctx, out.folded, (size_t)2 * n * d.Q * 8))) return rc;
+  // Declared after the DevOut temporaries, so it is destroyed BEFORE them: any early return below (a failed launch or
+  // CUDA call in the chunk loop) first waits for the lanes that were already forked — their kernels may still be writing
+  // the temporaries that the DevOut destructors hand back to the pool on the primary stream.
+  struct LaneGuard {
+    p2v_ctx *ctx;
+    bool armed = false;
+    ~LaneGuard() {
+      if (!armed) return;
+      for (int i = 1; i < P2V_MAX_DEPTH; i++) cudaStreamSynchronize(ctx->lane_stream[i]);
+      cudaStreamSynchronize(ctx->copy_stream);
+      cudaStreamSynchronize(ctx->stream);
+      cudaGetLastError();
+    }
+  } lane_guard{ctx};
   cudaStream_t streams[P2V_MAX_DEPTH];
   streams[0] = ctx->stream;
   for (int i = 1; i < P2V_MAX_DEPTH; i++) streams[i] = ctx->lane_stream[i];
   if (depth >= 2) {
     // fork: the other streams start after everything already queued on the primary one
     P2V_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+    lane_guard.armed = true;
     for (int i = 1; i < depth; i++) P2V_CUDA(ctx, cudaStreamWaitEvent(streams[i], ctx->fork_ev, 0));
   }
+  if (!src_dev) lane_guard.armed = true;  // the copy stream runs ahead of the primary one as well
   const bool timed = depth == 1;
   static const bool trace_on = getenv("P2V_TRACE") != nullptr;
   std::vector<TracePoint> trace;
@@ -437,6 +453,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
       P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane_join[i], 0));
     }
   }
+  lane_guard.armed = false;  // every lane is joined into the primary stream from here on
   double host_issued = host_ms();
   bool any_host = false;
   for (DevOut *o : {&o_ch, &o_comb, &o_eq, &o_status, &o_bits, &o_qs, &o_folded, &o_roots}) {

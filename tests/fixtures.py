@@ -74,11 +74,23 @@ def tamper_words(lay, shape):
     return t
 
 
-def tampered_batch(blob, lay, shape, n, seed=0, accept_every=4):
-    """n copies of `blob`; copy i is left intact iff i % accept_every == 0, else one word (cycled through the
-    tamper matrix, then random words) gets +delta mod p.  Returns (blobs [n][W], tamper_word int32[n], delta u64[n])."""
+def tamper_table(name):
+    """The tamper matrix of a fixture as committed data (tests/golden/<name>_tamper.json, written by
+    tests/golden/make_tamper_tables.py from `tamper_words`): lets a process that must not load the product (bench.py's
+    reference arm) build the SAME seeded batch."""
+    import json
+
+    with open(os.path.join(GOLDEN, "%s_tamper.json" % name)) as fh:
+        return json.load(fh)
+
+
+def tampered_batch_from_table(blob, table, n, seed=0, accept_every=4):
+    """n copies of `blob`; copy i is left intact iff i % accept_every == 0, else one word (cycled through the tamper
+    matrix `table` = {field name: word offset}, then random words) gets +delta mod p.
+    Returns (blobs [n][W], tamper_word int32[n], delta u64[n])."""
+    blob = np.asarray(blob, dtype=np.uint64)
     rng = np.random.default_rng(seed)
-    names = sorted(tamper_words(lay, shape).items())
+    names = sorted(table.items())
     words = np.full(n, -1, dtype=np.int32)
     deltas = np.zeros(n, dtype=np.uint64)
     k = 0
@@ -89,12 +101,17 @@ def tampered_batch(blob, lay, shape, n, seed=0, accept_every=4):
             words[i] = names[k][1]
             deltas[i] = 1
         else:
-            words[i] = rng.integers(0, lay.blob_words)
+            words[i] = rng.integers(0, len(blob))
             deltas[i] = rng.integers(1, P, dtype=np.uint64)
         k += 1
-    blobs = np.tile(np.asarray(blob, dtype=np.uint64), (n, 1))
+    blobs = np.tile(blob, (n, 1))
     for i in range(n):
         if words[i] >= 0:
             v = (int(blobs[i, words[i]]) % P + int(deltas[i])) % P
             blobs[i, words[i]] = v
     return blobs, words, deltas
+
+
+def tampered_batch(blob, lay, shape, n, seed=0, accept_every=4):
+    """`tampered_batch_from_table` with the tamper matrix computed from the product's layout."""
+    return tampered_batch_from_table(blob, tamper_words(lay, shape), n, seed, accept_every)

@@ -305,3 +305,70 @@ def test_differential_fuzz_of_the_two_proof_decoders(p2v):
         outs.append(r.stdout.split())
     assert outs[0] == outs[1]
     assert int(outs[0][1]) > 50 and int(outs[0][2]) > 500  # both accepted and rejected mutants occurred
+
+
+def test_committed_tamper_tables_match_the_layout(p2v):
+    """tests/golden/<name>_tamper.json (used by bench.py's reference arm, which must not load the product) == the tamper
+    matrix computed from the live layout."""
+    for name in fixtures.ACCEPTING:
+        shape, lay, vkey, blob = fixtures.load(name)
+        assert fixtures.tamper_table(name) == {k: int(v) for k, v in fixtures.tamper_words(lay, shape).items()}, name
+        a = fixtures.tampered_batch(blob, lay, shape, 40, seed=9)
+        b = fixtures.tampered_batch_from_table(blob, fixtures.tamper_table(name), 40, seed=9)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_shape_fields_are_range_checked(p2v):
+    """Every integer of a shape is checked before it enters an offset, a shift or a loop bound: values that
+    would overflow the layout, divide by zero on the device or wrap in a narrowing cast are refused, both for JSON input and
+    for a p2v_shape built by the caller."""
+    common = json.loads(fixtures.read("small6", "common"))
+    def refuse(mutate, codes=(-6, -5, -4)):
+        c = json.loads(json.dumps(common))
+        mutate(c)
+        with pytest.raises(p2v.P2VError) as e:
+            p2v.parse_common(json.dumps(c))
+        assert e.value.code in codes, str(e.value)
+    def both_cfg(key, val):
+        def f(c):
+            c["config"]["fri_config"][key] = val
+            c["fri_params"]["config"][key] = val
+        return f
+    refuse(both_cfg("cap_height", 31))          # 4 << 31 overflows an int
+    refuse(both_cfg("cap_height", 25))
+    refuse(both_cfg("num_query_rounds", 2**31 + 5))   # would wrap to a small positive int
+    refuse(both_cfg("num_query_rounds", 0))
+    refuse(lambda c: c["config"].__setitem__("num_wires", 2**32 + 20))
+    refuse(lambda c: c.__setitem__("num_public_inputs", 2**40))
+    refuse(lambda c: c["fri_params"].__setitem__("degree_bits", 40))
+    refuse(lambda c: c["selectors_info"]["groups"][0].__setitem__("end", 99))
+    # lookup tables with quotient_degree_factor 1: lookup_deg = 0 chunks (Plonk/Lookups.hs:57) -> refused, not divided by
+    lu = json.loads(fixtures.read("lookup6", "common"))
+    lu["quotient_degree_factor"] = 1
+    with pytest.raises(p2v.P2VError) as e:
+        p2v.parse_common(json.dumps(lu))
+    assert e.value.code == -6
+    # a shape handed over as a struct goes through the same checks
+    shape, lay, vkey, blob = fixtures.load("small6")
+    import copy, ctypes
+    bad = p2v.Shape.from_buffer_copy(bytes(shape))
+    bad.cap_height = 30
+    with pytest.raises(p2v.P2VError):
+        p2v.shape_layout(bad)
+    bad = p2v.Shape.from_buffer_copy(bytes(shape))
+    bad.num_gates = 1000
+    with pytest.raises(p2v.P2VError):
+        p2v.shape_layout(bad)
+
+
+def test_fast_scanner_leaves_leading_zeros_to_the_tape_reader(p2v):
+    """`007` is not a JSON number (aeson refuses it): the forward-scan fast path must not accept what the definition rejects."""
+    shape, lay, vkey, blob = fixtures.load("small6")
+    text = fixtures.read("small6", "proof")
+    pw = str(int(json.loads(text)["proof"]["opening_proof"]["pow_witness"]))
+    assert text.count('"pow_witness":' + pw) + text.count('"pow_witness": ' + pw) >= 1
+    bad = text.replace('"pow_witness":' + pw, '"pow_witness":00' + pw).replace('"pow_witness": ' + pw, '"pow_witness": 00' + pw)
+    with pytest.raises(p2v.P2VError) as e:
+        p2v.parse_proof(bad, shape)
+    assert e.value.code == -4
+

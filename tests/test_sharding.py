@@ -70,3 +70,27 @@ def test_shard_bounds_cover_the_batch(p2v):
             assert all(s[0] % 32 == 0 for s in spans if s[1] > s[0])
     flags = np.random.default_rng(0).random(77) < 0.5
     assert np.array_equal(p2v.unpack_bits(sharding.pack_bits(flags), 77), flags)
+
+
+def test_c_slicing_rule_equals_python(p2v):
+    """p2v_shard_slice_len / p2v_shard_bounds (csrc/sharded_api.cu) == sharding.slice_len / shard_bounds."""
+    from plonky2_verifier_b200 import sharding
+
+    for n in (0, 1, 31, 32, 33, 64, 1000, 32808, 100000, 10**6 + 7):
+        for world in (1, 2, 3, 4, 8):
+            assert p2v.shard_slice_len(n, world) == sharding.slice_len(n, world)
+            for r in range(world):
+                assert p2v.shard_bounds(n, r, world) == sharding.shard_bounds(n, r, world)
+    with pytest.raises(p2v.P2VError):
+        p2v.shard_bounds(10, 2, 2)
+
+
+def test_nccl_bootstrap_symbols_without_gpu(p2v):
+    """The communicator bootstrap is bound at run time: without libnccl the call fails cleanly, with it rank 0 gets 128 bytes."""
+    try:
+        uid = p2v.nccl_unique_id()
+    except p2v.P2VError as e:
+        assert e.code in (-6, -2)
+    else:
+        assert len(uid) == 128 and any(uid)
+
