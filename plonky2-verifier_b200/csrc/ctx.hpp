@@ -21,6 +21,9 @@ struct p2v_ctx {
   void *lane_ws[P2V_MAX_DEPTH] = {};             // [0] unused (= ws)
   size_t lane_ws_bytes[P2V_MAX_DEPTH] = {};
   cudaEvent_t lane_join[P2V_MAX_DEPTH] = {};
+  // per lane: K4/K5 (transcript, constraints) run on a side stream next to the leaf phase of the Merkle kernel
+  cudaStream_t side_stream[P2V_MAX_DEPTH] = {};
+  cudaEvent_t staged_ev[P2V_MAX_DEPTH] = {}, transcript_ev[P2V_MAX_DEPTH] = {};
   int pipeline = 4;                // 1 = strictly serial chunks (per-section timings valid), 2..P2V_MAX_DEPTH = overlapped
   cudaEvent_t fork_ev = nullptr;
   std::string err;

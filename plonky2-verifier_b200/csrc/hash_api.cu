@@ -12,6 +12,11 @@ static int ctxInit(p2v_ctx *ctx, int device) {
     P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->lane_stream[i], cudaStreamNonBlocking));
     P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->lane_join[i], cudaEventDisableTiming));
   }
+  for (int i = 0; i < P2V_MAX_DEPTH; i++) {
+    P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->side_stream[i], cudaStreamNonBlocking));
+    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->staged_ev[i], cudaEventDisableTiming));
+    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->transcript_ev[i], cudaEventDisableTiming));
+  }
   P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
   for (auto &ev : ctx->ev) P2V_CUDA(nullptr, cudaEventCreate(&ev));
   for (int i = 0; i < 2; i++) {
@@ -70,6 +75,11 @@ void p2v_ctx_destroy(p2v_ctx *ctx) {
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   for (int i = 1; i < P2V_MAX_DEPTH; i++)
     if (ctx->lane_stream[i]) cudaStreamSynchronize(ctx->lane_stream[i]);
+  for (int i = 0; i < P2V_MAX_DEPTH; i++) {
+    if (ctx->side_stream[i]) { cudaStreamSynchronize(ctx->side_stream[i]); cudaStreamDestroy(ctx->side_stream[i]); }
+    if (ctx->staged_ev[i]) cudaEventDestroy(ctx->staged_ev[i]);
+    if (ctx->transcript_ev[i]) cudaEventDestroy(ctx->transcript_ev[i]);
+  }
   p2v_nccl_finalize(ctx);
   if (ctx->ws) cudaFree(ctx->ws);
   for (int i = 1; i < P2V_MAX_DEPTH; i++) {
@@ -138,11 +148,7 @@ int p2v_poseidon_permute(p2v_ctx *ctx, const uint64_t *in, uint64_t *out, size_t
   int rc;
   if ((rc = din.init(ctx, in, n * 12 * sizeof(u64)))) return rc;
   if ((rc = dout.init(ctx, out, n * 12 * sizeof(u64)))) return rc;
-#if P2V_DUAL
-  P2V_LAUNCH(ctx, k_poseidon_permute2, p2v_grid_for(ctx, (n + 1) / 2, 128, 32), 128, 0, din.as<u64>(), dout.as<u64>(), n);
-#else
   P2V_LAUNCH(ctx, k_poseidon_permute, p2v_grid_for(ctx, n, 256, 16), 256, 0, din.as<u64>(), dout.as<u64>(), n);
-#endif
   if ((rc = dout.finish())) return rc;
   if (dout.host) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return P2V_OK;

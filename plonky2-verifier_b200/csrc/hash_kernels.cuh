@@ -17,28 +17,6 @@ __global__ void __launch_bounds__(256) k_poseidon_permute(const u64 *__restrict_
   }
 }
 
-// K1 in the dual form: a thread permutes states t and t + ceil(n/2) (poseidon_permute2); an odd n lets the last thread
-// permute its first state twice.
-__global__ void __launch_bounds__(128) k_poseidon_permute2(const u64 *__restrict__ in, u64 *__restrict__ out, size_t n) {
-  size_t half = (n + 1) / 2;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < half; t += stride) {
-    size_t t2 = t + half < n ? t + half : t;
-    u64 a[12], b[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-      a[i] = in[(size_t)i * n + t];
-      b[i] = in[(size_t)i * n + t2];
-    }
-    poseidon_permute2(a, b);
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-      out[(size_t)i * n + t] = gl_canon(a[i]);
-      if (t2 != t) out[(size_t)i * n + t2] = gl_canon(b[i]);
-    }
-  }
-}
-
 // Sponge over a strided column of words: word j of item t is at base[j*stride + t].
 // `sponge`, Hash/Sponge.hs:26-31: overwrite mode, rate 8, no padding, w = 0 -> zero digest.
 // Returns the state; digest = s[0..3] (lazy).

@@ -25,10 +25,6 @@
 #include "gl.cuh"
 #include "poseidon_constants.h"
 
-#ifndef P2V_DUAL
-/* 1: the kernels that hash many independent items (K1, K6a) give every thread TWO of them (poseidon_permute2) */
-#define P2V_DUAL 0
-#endif
 #ifndef POSEIDON_SBOX_GROUP
 /* s-boxes per iteration of the register-rotating loop of a full round: 3, 4, 6 or 12 (= no loop, no rotation moves).
  * With the 80-register budget of the Merkle kernel the fully unrolled form measured best (12: 82.3% of the roofline,
@@ -609,48 +605,3 @@ __device__ __forceinline__ void poseidon_permute(u64 (&s)[12]) {
   }
 #endif
 }
-
-// ---- two permutations per thread, half a round out of phase (POSEIDON dual form, round 2) -----------------------
-// ncu of the single form: a warp issues in order, and the s-box phases are dependent carry chains on the FMA pipe —
-// the lane-0 s-box of a partial round issued 6.6% of its cycles per warp (19% of the kernel's time for 7% of its
-// instructions), the twelve s-boxes of a full round 14%, the linear layer 28%.  Relieving the FMA pipe alone (layer on
-// FP64) moved the kernel by 3%: what is missing is independent work NEXT to the chains in each warp's own instruction
-// stream.  Here a thread carries two states A and B and runs A's linear layer L_r in the same basic block as B's s-box
-// S_r, then A's S_{r+1} next to B's L_r:  FMA-pipe chains of one hash are interleaved by ptxas with the FP64/ALU
-// work of the other, statically, and every block has two independent dependency chains.  Only one hash is inside a
-// layer at any time, so the cost is one more state (24 registers), not a second set of accumulators.
-//   slot 2r+1: A.L_r || B.S_r        slot 2r+2: A.S_{r+1} || B.L_r       (prologue A.S_0)
-// The eleven other s-boxes of a full round run in a block of their own (eleven independent chains).
-__device__ __forceinline__ void poseidon_permute2(u64 (&a)[12], u64 (&b)[12]) {
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    a[i] = gl_add(a[i], c_pt.rc[0][i]);
-    b[i] = gl_add(b[i], c_pt.rc[0][i]);
-  }
-#pragma unroll
-  for (int k = 0; k < 12; k++) a[k] = poseidon_sbox(a[k]);  // A.S_0
-#pragma unroll 1
-  for (int r = 0; r < 30; r++) {
-    const bool full_b = r < 4 || r >= 26;                       // kind of B.S_r
-    const bool full_a = (r + 1 < 4 || r + 1 >= 26) && r < 29;   // kind of A.S_{r+1} (none after the last round)
-    {  // A.L_r || B.S_r (lane 0)
-      u64 t = poseidon_sbox(b[0]);
-      poseidon_mds_layer(a, r + 1);
-      b[0] = t;
-    }
-    if (full_b) {
-#pragma unroll
-      for (int k = 1; k < 12; k++) b[k] = poseidon_sbox(b[k]);
-    }
-    {  // A.S_{r+1} (lane 0) || B.L_r ; after the last round A is finished: the s-box result is dropped (one select)
-      u64 t = poseidon_sbox(a[0]);
-      poseidon_mds_layer(b, r + 1);
-      a[0] = r == 29 ? a[0] : t;
-    }
-    if (full_a) {
-#pragma unroll
-      for (int k = 1; k < 12; k++) a[k] = poseidon_sbox(a[k]);
-    }
-  }
-}
-

@@ -139,13 +139,14 @@ size_t carve(const DevCircuit &d, size_t m, char *base, Workspace *ws, bool want
   u64 *comb = (u64 *)take((size_t)2 * d.r * m * 8);
   u32 *qstat = (u32 *)take((size_t)d.Q * m * 4);
   uint8_t *tree_ok = (uint8_t *)take((size_t)(4 + d.nsteps) * d.Q * m);
+  u64 *leafdig = (u64 *)take((size_t)4 * (4 + d.nsteps) * d.Q * m * 8);
   u64 *folded = want_folded ? (u64 *)take((size_t)2 * d.Q * m * 8) : nullptr;
   uint8_t *eq = (uint8_t *)take(m);
   u64 *roots = want_roots ? (u64 *)take((size_t)4 * (4 + d.nsteps) * d.Q * m * 8) : nullptr;
   if (ws) {
     ws->roots = roots; ws->ch_in = nullptr; ws->ch_in_n = 0; ws->ch_in_off = 0;
     ws->pp = pp; ws->qp = qp; ws->ch = ch; ws->pih = pih; ws->pre = pre; ws->apow = apow; ws->comb = comb; ws->qstat = qstat;
-    ws->folded = folded; ws->eqmask = eq; ws->tree_ok = tree_ok;
+    ws->folded = folded; ws->eqmask = eq; ws->tree_ok = tree_ok; ws->leafdig = leafdig;
   }
   return off;
 }
@@ -157,6 +158,7 @@ int ensureWorkspace(p2v_ctx *ctx, int which, size_t bytes) {
   if (ws) {
     P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 1; i < P2V_MAX_DEPTH; i++) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->lane_stream[i]));
+    for (int i = 0; i < P2V_MAX_DEPTH; i++) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->side_stream[i]));
     cudaFree(ws);
     ws = nullptr;
     have = 0;
@@ -324,6 +326,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     bool armed = false;
     ~LaneGuard() {
       if (!armed) return;
+      for (int i = 0; i < P2V_MAX_DEPTH; i++) cudaStreamSynchronize(ctx->side_stream[i]);
       for (int i = 1; i < P2V_MAX_DEPTH; i++) cudaStreamSynchronize(ctx->lane_stream[i]);
       cudaStreamSynchronize(ctx->copy_stream);
       cudaStreamSynchronize(ctx->stream);
@@ -341,6 +344,7 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   }
   if (!src_dev) lane_guard.armed = true;  // the copy stream runs ahead of the primary one as well
   const bool timed = depth == 1;
+  static const bool no_split = getenv("P2V_NO_SPLIT") != nullptr;  // A/B aid: the Merkle kernel in one launch after K4/K5
   static const bool trace_on = getenv("P2V_TRACE") != nullptr;
   std::vector<TracePoint> trace;
   auto mark = [&](const char *what, int chunk_i, size_t m_i, cudaStream_t s) {
@@ -397,35 +401,44 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     if (!src_dev) P2V_CUDA(ctx, cudaEventRecord(ctx->compute_done[b], st));
     mark("k0_end", k, m, st);
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-    // K4
-    P2V_LAUNCH_ON(ctx, st, k_challenges, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
-    if (d.num_lookup_polys > 0) P2V_LAUNCH_ON(ctx, st, k_lookup_delta_copies, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m);
+    // K4 + K5 on the lane's side stream when the Merkle kernel runs in two phases: the leaf phase needs nothing from the
+    // transcript, so the per-proof chains of K4/K5 (latency-bound, ~5 ms per chunk whatever its size) hide beside it
+    const bool split = (what & RUN_FRI) && !no_split;
+    cudaStream_t side = (split && depth >= 2) ? ctx->side_stream[lane] : st;
+    if (side != st) {
+      P2V_CUDA(ctx, cudaEventRecord(ctx->staged_ev[lane], st));
+      P2V_CUDA(ctx, cudaStreamWaitEvent(side, ctx->staged_ev[lane], 0));
+    }
+    P2V_LAUNCH_ON(ctx, side, k_challenges, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
+    if (d.num_lookup_polys > 0) P2V_LAUNCH_ON(ctx, side, k_lookup_delta_copies, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m);
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     // K5
-    if (what & RUN_CONSTRAINTS) P2V_LAUNCH_ON(ctx, st, k_constraints, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
+    if (what & RUN_CONSTRAINTS) P2V_LAUNCH_ON(ctx, side, k_constraints, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-    mark("k5_end", k, m, st);
+    if (side != st) P2V_CUDA(ctx, cudaEventRecord(ctx->transcript_ev[lane], side));
+    mark("k5_end", k, m, side);
     // K6
     if (what & RUN_FRI) {
       size_t items = m * (size_t)d.Q * (4 + d.nsteps);
       // serial mode: persistent grid of 256-thread blocks; pipelined mode: one 128-thread block per 128 openings, so
       // that blocks of all lanes' kernels interleave on the SMs as resources free up
-#if P2V_DUAL
-      {
-        size_t pairs = ((m + 1) / 2) * (size_t)d.Q * (4 + d.nsteps);
-        unsigned grid = depth >= 2 ? (unsigned)((pairs + P2V_MERKLE_DUAL_BLOCK - 1) / P2V_MERKLE_DUAL_BLOCK)
-                                   : (unsigned)p2v_grid_for(ctx, pairs, P2V_MERKLE_DUAL_BLOCK, P2V_MERKLE_DUAL_MINBLOCKS);
-        P2V_LAUNCH_ON(ctx, st, (k_fri_merkle_dual<P2V_MERKLE_DUAL_BLOCK, P2V_MERKLE_DUAL_MINBLOCKS>), grid, P2V_MERKLE_DUAL_BLOCK, 0, d, ws, m);
-      }
-#else
-      if (depth >= 2) {
-        unsigned grid = (unsigned)((items + P2V_MERKLE_BLOCK_PIPE - 1) / P2V_MERKLE_BLOCK_PIPE);
-        P2V_LAUNCH_ON(ctx, st, (k_fri_merkle<P2V_MERKLE_BLOCK_PIPE, P2V_MERKLE_MINBLOCKS_PIPE>), grid, P2V_MERKLE_BLOCK_PIPE, 0, d, ws, m);
+      const bool pipe = depth >= 2;
+      unsigned grid = pipe ? (unsigned)((items + P2V_MERKLE_BLOCK_PIPE - 1) / P2V_MERKLE_BLOCK_PIPE)
+                           : (unsigned)p2v_grid_for(ctx, items, P2V_MERKLE_BLOCK, P2V_MERKLE_MINBLOCKS);
+#define P2V_MERKLE_LAUNCH(PHASE)                                                                                                                          \
+  do {                                                                                                                                                  \
+    if (pipe) P2V_LAUNCH_ON(ctx, st, (k_fri_merkle<P2V_MERKLE_BLOCK_PIPE, P2V_MERKLE_MINBLOCKS_PIPE, PHASE>), grid, P2V_MERKLE_BLOCK_PIPE, 0, d, ws, m); \
+    else P2V_LAUNCH_ON(ctx, st, (k_fri_merkle<P2V_MERKLE_BLOCK, P2V_MERKLE_MINBLOCKS, PHASE>), grid, P2V_MERKLE_BLOCK, 0, d, ws, m);                     \
+  } while (0)
+      if (split) {
+        P2V_MERKLE_LAUNCH(MERKLE_LEAF);
+        if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
+        if (side != st) P2V_CUDA(ctx, cudaStreamWaitEvent(st, ctx->transcript_ev[lane], 0));
+        P2V_MERKLE_LAUNCH(MERKLE_PATH);
       } else {
-        unsigned grid = (unsigned)p2v_grid_for(ctx, items, P2V_MERKLE_BLOCK, P2V_MERKLE_MINBLOCKS);
-        P2V_LAUNCH_ON(ctx, st, (k_fri_merkle<P2V_MERKLE_BLOCK, P2V_MERKLE_MINBLOCKS>), grid, P2V_MERKLE_BLOCK, 0, d, ws, m);
+        P2V_MERKLE_LAUNCH(MERKLE_ALL);
       }
-#endif
+#undef P2V_MERKLE_LAUNCH
       if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
       P2V_LAUNCH_ON(ctx, st, k_fri_query, p2v_grid_for(ctx, m * d.Q, 256, 4), 256, 0, d, ws, m);
     }
@@ -496,6 +509,8 @@ static int resolveTimings(p2v_ctx *ctx) {
   {  // "fri" = k_fri_merkle + k_fri_query; the Merkle part separately (only valid if FRI ran)
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[6]) == cudaSuccess) ctx->last_ms["fri_merkle"] = ms;
+    else cudaGetLastError();
+    if (cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[7]) == cudaSuccess) ctx->last_ms["fri_merkle_leaf"] = ms;
     else cudaGetLastError();
   }
   return P2V_OK;

@@ -64,6 +64,7 @@ struct Workspace {
   u64 *comb;   // [2r][n]         combined constraints
   u32 *qstat;  // [Q][n]          per-query status
   uint8_t *tree_ok;  // [4+nsteps][Q][n]  Merkle opening verdicts (K6a -> K6b)
+  u64 *leafdig;      // [4][(4+nsteps)*Q*n]  leaf digests (K6a leaf phase -> K6a path phase)
   u64 *folded; // [2][Q*n]        final folded evaluation per query (debug/parity output)
   uint8_t *eqmask;  // [n]        bit j: round j of the quotient identity holds
   u64 *roots;  // [4][(4+nsteps)*Q*n]  recomputed Merkle roots of every opening (debug/parity output, else NULL)
@@ -303,7 +304,12 @@ __global__ void __launch_bounds__(128) k_challenges(const __grid_constant__ DevC
 #ifndef P2V_MERKLE_MINBLOCKS_PIPE
 #define P2V_MERKLE_MINBLOCKS_PIPE 5
 #endif
-template <int BLOCK, int MINBLOCKS>
+// PHASE: the kernel runs in two launches per chunk.  The leaf sponges (43% of the permutations at the standard shape)
+// need nothing from the transcript, so PHASE 1 starts right after K0 while K4/K5 of the same chunk — one thread per proof,
+// a 114-permutation dependent chain, ~5 ms whatever the chunk size — run beside it on the lane's side stream; PHASE 2
+// (the sibling compressions, which need the query indices) follows when both are done.  PHASE 0 = both in one launch.
+enum { MERKLE_ALL = 0, MERKLE_LEAF = 1, MERKLE_PATH = 2 };
+template <int BLOCK, int MINBLOCKS, int PHASE>
 __global__ void __launch_bounds__(BLOCK, MINBLOCKS) k_fri_merkle(const __grid_constant__ DevCircuit c, Workspace ws, size_t n) {
   const int Q = c.Q;
   const size_t per_tree = n * (size_t)Q;
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) k_fri_merkle(const __grid_co
     int q = (int)(rem / n);
     size_t p = rem - (size_t)q * n;
     const u64 *__restrict__ qbase = qp + rem;
-    u32 index = (u32)ws.ch[(size_t)(c.ch_idx + q) * n + p];
+    u32 index = PHASE == MERKLE_LEAF ? 0u : (u32)ws.ch[(size_t)(c.ch_idx + q) * n + p];  // the leaf phase must not touch K4's output
     int leaf_off, width, sib_off, plen, cap_off;
     if (tr < 4) {
       leaf_off = L.q_off_leaf[tr]; width = L.oracle_width[tr]; sib_off = L.q_off_sibs[tr]; plen = L.init_path_len;
@@ -334,10 +340,15 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) k_fri_merkle(const __grid_co
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = 0;
     int nblk = (width + 7) >> 3;
-    int iters = nblk + plen;
+    int iters = PHASE == MERKLE_LEAF ? nblk : nblk + plen;
+    int it0 = PHASE == MERKLE_PATH ? nblk : 0;
+    if (PHASE == MERKLE_PATH) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) s[i] = ws.leafdig[(size_t)i * total + t];
+    }
 #pragma unroll 1
-    for (int it = 0; it < iters; it++) {
-      if (it < nblk) {
+    for (int it = it0; it < iters; it++) {
+      if (PHASE != MERKLE_PATH && (PHASE == MERKLE_LEAF || it < nblk)) {
         // sponge block, Hash/Sponge.hs:26-31 (overwrite the first k lanes)
         int k = width - it * 8;
         const u64 *src = qbase + (size_t)(leaf_off + it * 8) * qstride;
@@ -360,6 +371,11 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) k_fri_merkle(const __grid_co
       }
       poseidon_permute(s);
     }
+    if (PHASE == MERKLE_LEAF) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) ws.leafdig[(size_t)i * total + t] = s[i];
+      continue;
+    }
     // compare with cap[index] (Merkle.hs:39-42); cap 0 is the verifier key, the others come with the proof
     bool ok = index < (1u << c.cap_height);
     u32 ci = ok ? index : 0;
@@ -372,105 +388,6 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) k_fri_merkle(const __grid_co
     if (ws.roots) {
 #pragma unroll
       for (int i = 0; i < 4; i++) ws.roots[(size_t)i * total + t] = gl_canon(s[i]);
-    }
-  }
-}
-
-// K6a in the dual form (P2V_DUAL): thread t = (tree, q, pair of proofs 2i, 2i+1); the two openings belong to the same tree
-// and query slot, so they take the same number of permutations and run in lockstep through poseidon_permute2.  An odd
-// chunk size lets the last pair hash proof n-1 twice (written once).
-#ifndef P2V_MERKLE_DUAL_BLOCK
-#define P2V_MERKLE_DUAL_BLOCK 128
-#endif
-#ifndef P2V_MERKLE_DUAL_MINBLOCKS
-#define P2V_MERKLE_DUAL_MINBLOCKS 3
-#endif
-template <int BLOCK, int MINBLOCKS>
-__global__ void __launch_bounds__(BLOCK, MINBLOCKS) k_fri_merkle_dual(const __grid_constant__ DevCircuit c, Workspace ws, size_t n) {
-  const int Q = c.Q;
-  const size_t half = (n + 1) / 2;
-  const size_t per_tree = n * (size_t)Q;
-  const size_t pairs_per_tree = half * (size_t)Q;
-  const size_t total = pairs_per_tree * (size_t)(4 + c.nsteps);
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const u64 *__restrict__ pp = ws.pp;
-  const u64 *__restrict__ qp = ws.qp;
-  const p2v_layout &L = c.L;
-  const size_t qstride = per_tree;  // word w of (q, proof) at qp[w*Q*n + q*n + proof]
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-    int tr = (int)(t / pairs_per_tree);
-    size_t rem = t - (size_t)tr * pairs_per_tree;  // = q*half + pair
-    int q = (int)(rem / half);
-    size_t pa = 2 * (rem - (size_t)q * half);
-    size_t pb = pa + 1 < n ? pa + 1 : pa;
-    const u64 *__restrict__ qa = qp + (size_t)q * n + pa;
-    const u64 *__restrict__ qb = qp + (size_t)q * n + pb;
-    u32 ia = (u32)ws.ch[(size_t)(c.ch_idx + q) * n + pa], ib = (u32)ws.ch[(size_t)(c.ch_idx + q) * n + pb];
-    int leaf_off, width, sib_off, plen, cap_off;
-    if (tr < 4) {
-      leaf_off = L.q_off_leaf[tr]; width = L.oracle_width[tr]; sib_off = L.q_off_sibs[tr]; plen = L.init_path_len;
-      cap_off = tr == 1 ? L.off_wires_cap : tr == 2 ? L.off_zs_pp_cap : L.off_quotient_cap;
-    } else {
-      int st = tr - 4;
-      leaf_off = L.q_off_step_evals[st]; width = 2 << c.arity_bits[st]; sib_off = L.q_off_step_sibs[st]; plen = L.step_path_len[st];
-      ia >>= c.cum_bits[st + 1];
-      ib >>= c.cum_bits[st + 1];
-      cap_off = L.off_commit_caps + st * L.cap_words;
-    }
-    u64 a[12], b[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) a[i] = b[i] = 0;
-    int nblk = (width + 7) >> 3;
-    int iters = nblk + plen;
-#pragma unroll 1
-    for (int it = 0; it < iters; it++) {
-      if (it < nblk) {
-        int k = width - it * 8;
-        size_t off = (size_t)(leaf_off + it * 8) * qstride;
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-          if (i < k) {
-            a[i] = qa[off + (size_t)i * qstride];
-            b[i] = qb[off + (size_t)i * qstride];
-          }
-      } else {
-        size_t off = (size_t)(sib_off + (it - nblk) * 4) * qstride;
-        bool ea = (ia & 1u) == 0, eb = (ib & 1u) == 0;
-        ia >>= 1;
-        ib >>= 1;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          u64 sa = qa[off + (size_t)i * qstride], sb = qb[off + (size_t)i * qstride];
-          u64 na = a[i], nb = b[i];
-          a[i] = ea ? na : sa;
-          a[4 + i] = ea ? sa : na;
-          a[8 + i] = 0;
-          b[i] = eb ? nb : sb;
-          b[4 + i] = eb ? sb : nb;
-          b[8 + i] = 0;
-        }
-      }
-      poseidon_permute2(a, b);
-    }
-    bool oka = ia < (1u << c.cap_height), okb = ib < (1u << c.cap_height);
-    u32 ca = oka ? ia : 0, cb = okb ? ib : 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      u64 wa = tr == 0 ? __ldg(c.vkey + ca * 4 + i) : pp[(size_t)(cap_off + ca * 4 + i) * n + pa];
-      u64 wb = tr == 0 ? __ldg(c.vkey + cb * 4 + i) : pp[(size_t)(cap_off + cb * 4 + i) * n + pb];
-      oka = oka && (gl_canon(a[i]) == gl_canon(wa));
-      okb = okb && (gl_canon(b[i]) == gl_canon(wb));
-    }
-    size_t base = (size_t)tr * per_tree + (size_t)q * n;
-    ws.tree_ok[base + pa] = oka ? 1 : 0;
-    if (pb != pa) ws.tree_ok[base + pb] = okb ? 1 : 0;
-    if (ws.roots) {
-      const size_t all = per_tree * (size_t)(4 + c.nsteps);
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        ws.roots[(size_t)i * all + base + pa] = gl_canon(a[i]);
-        if (pb != pa) ws.roots[(size_t)i * all + base + pb] = gl_canon(b[i]);
-      }
     }
   }
 }
