@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define P2V_ABI_VERSION 1
+#define P2V_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------ */
 #define P2V_OK 0
@@ -49,13 +49,14 @@ extern "C" {
 #define P2V_E_UNSUPPORTED (-6) /* reference `error` sites for unsupported features */
 #define P2V_E_NOMEM (-7)
 
-/* ---- limits of the fixed-size shape record ----------------------------------- */
-#define P2V_MAX_GATES 32
-#define P2V_MAX_GROUPS 8
-#define P2V_MAX_ROUTED 128
-#define P2V_MAX_STEPS 8
-#define P2V_MAX_LUTS 8
-#define P2V_MAX_WEIGHTS 64
+/* ---- limits of the fixed-size shape record (ABI 2: twice to four times the sizes of ABI 1; Types.hs:47-70 has unbounded
+ * lists — a circuit beyond these limits is refused with P2V_E_UNSUPPORTED, never truncated) ------------------------- */
+#define P2V_MAX_GATES 64
+#define P2V_MAX_GROUPS 16
+#define P2V_MAX_ROUTED 256
+#define P2V_MAX_STEPS 16
+#define P2V_MAX_LUTS 16
+#define P2V_MAX_WEIGHTS 256
 
 /* Gate kinds: the constructors of `data Gate`, Gate/Base.hs:27-45. */
 enum p2v_gate_kind {
@@ -289,12 +290,15 @@ typedef struct p2v_intermediates {
 int p2v_verify_intermediates(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t n, const p2v_intermediates *io);
 
 /* Heterogeneous batches: proofs of DIFFERENT circuits (other degree_bits, gate sets, FRI parameters,
- * lookups ...) grouped by circuit; group g is verified exactly like p2v_verify_batch(ctx, circuits[g], blobs[g],
- * counts[g], accept_bits[g], status[g]) — `map (uncurry verifyProof)` over (vkey, proof) pairs that do not share a
- * vkey.  Groups run back to back on the context's pipeline; a kernel launch is shape-homogeneous by construction
- * (the circuit is a kernel parameter).  Stops at the first group that fails with an error code. */
+ * lookups ...) grouped by circuit; group g gets exactly the verdicts of p2v_verify_batch(ctx, circuits[g], blobs[g],
+ * counts[g], accept_bits[g], status[g]) — `map (uncurry verifyProof)` over (vkey, proof) pairs that do not share a vkey.
+ * The chunks of ALL groups share the lanes of the context's pipeline, so many small groups run side by side (a kernel
+ * launch is shape-homogeneous because the circuit is a kernel parameter; the call is not).  A group that cannot run (NULL
+ * pointer, circuit of another context, oversized blob) does not stop the others: rcs[g] (may be NULL) receives each
+ * group's P2V_OK / error code and the call returns the first group error (P2V_OK if none). */
 int p2v_verify_groups(p2v_ctx *ctx, size_t n_groups, const p2v_circuit *const *circuits, const uint64_t *const *blobs,
-                      const size_t *counts, uint32_t *const *accept_bits, uint32_t *const *status);
+                      const size_t *counts, uint32_t *const *accept_bits, uint32_t *const *status, int32_t *rcs);
+
 /* ---- multi-GPU: one process per GPU, contiguous slices, ONE all-gather of the accept bitmap ------ */
 /* The slicing rule.  slice_len = ceil(n_total / world) rounded up to a multiple of 32 (bitmap words never straddle two
  * ranks); rank r owns proofs [min(n_total, r*slice_len), min(n_total, (r+1)*slice_len)) — the last ranks may be short

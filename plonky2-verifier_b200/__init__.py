@@ -22,12 +22,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # P2V_LIB_PATH: tuning aid only (tools/variants_prebuilt.sh loads compile-time variants of the same library)
 LIB_PATH = os.environ.get("P2V_LIB_PATH") or os.path.join(_HERE, "libp2v.so")
 
-P2V_MAX_GATES = 32
-P2V_MAX_GROUPS = 8
-P2V_MAX_ROUTED = 128
-P2V_MAX_STEPS = 8
-P2V_MAX_LUTS = 8
-P2V_MAX_WEIGHTS = 64
+P2V_MAX_GATES = 64
+P2V_MAX_GROUPS = 16
+P2V_MAX_ROUTED = 256
+P2V_MAX_STEPS = 16
+P2V_MAX_LUTS = 16
+P2V_MAX_WEIGHTS = 256
 
 GATE_KINDS = [
     "ArithmeticGate", "ArithmeticExtensionGate", "BaseSumGate", "CosetInterpolationGate", "ConstantGate",
@@ -143,7 +143,7 @@ def lib():
         "p2v_constraints": (C.c_int, [vp, vp, u64p, sz, u64p, u8p]),
         "p2v_fri": (C.c_int, [vp, vp, u64p, sz, u32p, u32p, u64p]),
         "p2v_verify_batch": (C.c_int, [vp, vp, u64p, sz, u32p, u32p]),
-        "p2v_verify_groups": (C.c_int, [vp, sz, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(vp)]),
+        "p2v_verify_groups": (C.c_int, [vp, sz, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz), C.POINTER(vp), C.POINTER(vp), C.c_void_p]),
         "p2v_ctx_set_chunk": (C.c_int, [vp, sz]),
         "p2v_ctx_set_pipeline": (C.c_int, [vp, C.c_int]),
         "p2v_synth_batch": (C.c_int, [vp, vp, u64p, sz, C.c_void_p, u64p, u64p]),
@@ -464,17 +464,25 @@ def shard_bounds(n_total, rank, world):
     return a.value, b.value
 
 
-def verify_groups(ctx, groups):
+def verify_groups(ctx, groups, return_codes=False):
     """Heterogeneous batch: groups = [(Circuit, blobs), ...] with a different circuit per group ->
-    [(accept bool[n_g], status u32[n_g]), ...]  (p2v_verify_groups)."""
+    [(accept bool[n_g], status u32[n_g]), ...]  (p2v_verify_groups; the groups' chunks share the pipeline lanes).
+    With return_codes=True a group that cannot run is reported in the second result (per-group error codes) instead of
+    raising; its verdicts are all-reject."""
     k = len(groups)
-    ns = [c._n(b, None) for c, b in groups]
+    ns = [c._n(b, None) if c is not None and b is not None else 0 for c, b in groups]
     bits = [np.zeros((n + 31) // 32, dtype=np.uint32) for n in ns]
-    status = [np.empty(n, dtype=np.uint32) for n in ns]
+    status = [np.full(n, 0xFFFFFFFF, dtype=np.uint32) for n in ns]
+    rcs = np.zeros(k, dtype=np.int32)
     arr = lambda ptrs: (C.c_void_p * k)(*ptrs)
-    ctx._check(lib().p2v_verify_groups(ctx._h, k, arr([c._h for c, _ in groups]), arr([_ptr(b) for _, b in groups]),
-                                       (C.c_size_t * k)(*ns), arr([_ptr(x) for x in bits]), arr([_ptr(x) for x in status])))
-    return [(unpack_bits(bits[g], ns[g]), status[g]) for g in range(k)]
+    rc = lib().p2v_verify_groups(ctx._h, k, arr([c._h if c is not None else None for c, _ in groups]),
+                                 arr([_ptr(b) if b is not None else None for _, b in groups]), (C.c_size_t * k)(*ns),
+                                 arr([_ptr(x) for x in bits]), arr([_ptr(x) for x in status]), rcs.ctypes.data)
+    out = [(unpack_bits(bits[g], ns[g]), status[g]) for g in range(k)]
+    if return_codes:
+        return out, rcs
+    ctx._check(rc)
+    return out
 
 
 def unpack_bits(words, n):

@@ -422,6 +422,7 @@ constexpr PoseidonRcCrt64 poseidon_make_rc_crt64() {
 }
 static __constant__ PoseidonRcCrt64 c_rc64 = poseidon_make_rc_crt64();
 
+
 // contribution of input pair J to rows I..5 (column-major: a pair can be accumulated as soon as its two s-boxes are done)
 template <int J, int I>
 __device__ __forceinline__ void poseidon_crt64_col(double (&SL)[6], double (&DL)[6], double (&SH)[6], double (&DH)[6], double xpL,

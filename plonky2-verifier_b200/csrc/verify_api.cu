@@ -82,6 +82,7 @@ void buildTranscript(DevCircuit &d) {
   const p2v_layout &L = d.L;
   int n = 0;
   auto add = [&](int kind, int off, int count, int dst) {
+    if (n >= P2V_MAX_TOPS) { n++; return; }  // counted, reported by the caller (cannot happen within P2V_MAX_STEPS)
     d.ops[n].kind = kind; d.ops[n].off = off; d.ops[n].count = count; d.ops[n].dst = dst;
     n++;
   };
@@ -270,55 +271,96 @@ struct TracePoint { const char *what; int chunk; size_t m; cudaEvent_t ev; };
 #define P2V_RAMP_START_DIV 8
 #endif
 
-int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t n, int what, Outputs out) {
-  auto host_t0 = std::chrono::steady_clock::now();
-  auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
-  if (!ctx || !cir || !blobs) return p2v_fail(ctx, P2V_E_INVALID, "NULL argument");
-  if (cir->ctx != ctx) return p2v_fail(ctx, P2V_E_INVALID, "circuit belongs to another context");
-  if (n == 0) return P2V_OK;
-  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
-  const DevCircuit &d = cir->dev;
-  const size_t blob_words = (size_t)d.L.blob_words;
-  if ((blob_words + 31) / 32 > 65535) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "proof blob longer than 2^21 words (K0 tiles words along grid.y)");
-  bool src_dev = p2v_is_device_ptr(blobs);
-  // Chunking.  Serial mode: as few chunks as memory allows.  Pipelined mode (default): chunks go round-robin over
-  // `pipeline` lanes (stream + workspace each), so K0+K4+K5 of the next chunks (latency-bound, one thread per proof)
-  // fill the GPU next to the Merkle kernel of the current one.  Device-resident input: ~3 GiB chunks.  Host input:
-  // ~0.5 GiB chunks — a chunk cannot start before it has arrived, PCIe delivers proofs only ~1.1x faster than the
-  // GPU verifies them, so there is never a backlog of big chunks to overlap; small constant chunks on 3 lanes
-  // measured 370 k proofs/s end to end against 348 k for 2 GiB chunks behind a ramp (tools/chunk_sweep.sh).
-  size_t chunk = ctx->chunk;
-  if (chunk == 0) {
-    size_t budget = ctx->pipeline > 1 ? (src_dev ? ((size_t)3 << 30) : ((size_t)512 << 20)) : (src_dev ? ((size_t)16 << 30) : ((size_t)2 << 30));
-    chunk = budget / (blob_words * 8);
-    if (chunk < 1024) chunk = 1024;
-  }
-  chunk = (chunk + 31) / 32 * 32;
-  if (chunk > n) chunk = (n + 31) / 32 * 32;
-  const int depth = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->pipeline, (n + chunk - 1) / chunk));
-  bool want_folded = out.folded != nullptr, want_roots = out.roots != nullptr;
-  size_t ws_bytes = carve(d, chunk, nullptr, nullptr, want_folded, want_roots);
-  int rc;
-  Workspace wsp[P2V_MAX_DEPTH];
-  for (int k = 0; k < depth; k++) {
-    if ((rc = ensureWorkspace(ctx, k, ws_bytes))) return rc;
-    carve(d, chunk, (char *)(k == 0 ? ctx->ws : ctx->lane_ws[k]), &wsp[k], want_folded, want_roots);
-  }
-  if (!src_dev && (rc = ensureStage(ctx, chunk * blob_words * 8))) return rc;
-
-  // outputs that may live on the host (temporaries are allocated in stream order on the primary stream)
+// One unit of work of a batch call: n proofs of ONE circuit.  p2v_verify_batch & co. run a single job; p2v_verify_groups
+// runs one job per circuit, and the chunks of all jobs share the lanes of the pipeline (a kernel launch is shape-homogeneous
+// because the circuit is a kernel parameter, a batch call need not be).
+struct Job {
+  const p2v_circuit *cir = nullptr;
+  const uint64_t *blobs = nullptr;
+  size_t n = 0;
+  Outputs out;
+  int rc = P2V_OK;       // per-job result: a job that cannot run does not stop the others
+  std::string err;
+};
+struct JobState {  // everything runJobs keeps per job while the chunks are in flight
+  bool src_dev = false;
+  size_t chunk = 0, blob_words = 0;
   DevOut o_ch, o_comb, o_eq, o_status, o_bits, o_qs, o_folded, o_roots;
   DevIn i_ch;
-  if ((rc = i_ch.init(ctx, out.challenges_in, (size_t)d.ch_words * n * 8))) return rc;
-  if ((rc = o_roots.init(ctx, out.roots, (size_t)4 * (4 + d.nsteps) * n * d.Q * 8))) return rc;
-  if ((rc = o_ch.init(ctx, out.challenges, (size_t)d.ch_words * n * 8))) return rc;
-  if ((rc = o_comb.init(ctx, out.combined, (size_t)2 * d.r * n * 8))) return rc;
-  if ((rc = o_eq.init(ctx, out.eqmask, n))) return rc;
-  if ((rc = o_status.init(ctx, out.status, n * 4))) return rc;
-  if ((rc = o_bits.init(ctx, out.accept_bits, (n + 31) / 32 * 4))) return rc;
-  if ((rc = o_qs.init(ctx, out.qstatus, n * d.Q * 4))) return rc;
-  if ((rc = o_folded.init(ctx, out.folded, (size_t)2 * n * d.Q * 8))) return rc;
-  // Declared after the DevOut temporaries, so it is destroyed BEFORE them: any early return below (a failed launch or
+};
+struct Chunk { int job; size_t c0, m; };
+
+int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
+  auto host_t0 = std::chrono::steady_clock::now();
+  auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+  if (!ctx) return p2v_fail(ctx, P2V_E_INVALID, "NULL argument");
+  P2V_CUDA(ctx, cudaSetDevice(ctx->device));
+  // ---- per-job validation and chunking -----------------------------------------------------------------------------
+  // Serial mode: as few chunks as memory allows.  Pipelined mode (default): chunks go round-robin over `pipeline` lanes
+  // (stream + workspace each).  Device-resident input: ~3 GiB chunks.  Host input: ~0.5 GiB chunks — a chunk cannot start
+  // before it has arrived and PCIe delivers proofs about as fast as the GPU verifies them, so there is never a backlog of
+  // big chunks to overlap (tools/chunk_sweep.sh).
+  std::vector<JobState> js(jobs.size());
+  auto reject = [&](Job &j, int code, const std::string &msg) { j.rc = code; j.err = msg; };
+  size_t total_chunks = 0;
+  for (size_t g = 0; g < jobs.size(); g++) {
+    Job &j = jobs[g];
+    JobState &t = js[g];
+    if (j.n == 0) continue;
+    if (!j.cir || !j.blobs) { reject(j, P2V_E_INVALID, "NULL argument"); continue; }
+    if (j.cir->ctx != ctx) { reject(j, P2V_E_INVALID, "circuit belongs to another context"); continue; }
+    t.blob_words = (size_t)j.cir->dev.L.blob_words;
+    if ((t.blob_words + 31) / 32 > 65535) { reject(j, P2V_E_UNSUPPORTED, "proof blob longer than 2^21 words (K0 tiles words along grid.y)"); continue; }
+    t.src_dev = p2v_is_device_ptr(j.blobs);
+    size_t chunk = ctx->chunk;
+    if (chunk == 0) {
+      size_t budget = ctx->pipeline > 1 ? (t.src_dev ? ((size_t)3 << 30) : ((size_t)512 << 20)) : (t.src_dev ? ((size_t)16 << 30) : ((size_t)2 << 30));
+      chunk = budget / (t.blob_words * 8);
+      if (chunk < 1024) chunk = 1024;
+    }
+    chunk = (chunk + 31) / 32 * 32;
+    if (chunk > j.n) chunk = (j.n + 31) / 32 * 32;
+    t.chunk = chunk;
+    total_chunks += (j.n + chunk - 1) / chunk;
+  }
+  auto live = [&](size_t g) { return jobs[g].rc == P2V_OK && jobs[g].n > 0; };
+  auto first_error = [&]() {
+    for (auto &j : jobs)
+      if (j.rc != P2V_OK) return p2v_fail(ctx, j.rc, j.err);
+    return (int)P2V_OK;
+  };
+  if (total_chunks == 0) return first_error();
+  const int depth = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->pipeline, total_chunks));
+  // ---- workspaces: one per lane, sized for the largest job ---------------------------------------------------------------
+  size_t ws_bytes = 0, stage_bytes = 0;
+  for (size_t g = 0; g < jobs.size(); g++) {
+    if (!live(g)) continue;
+    const DevCircuit &d = jobs[g].cir->dev;
+    ws_bytes = std::max(ws_bytes, carve(d, js[g].chunk, nullptr, nullptr, jobs[g].out.folded != nullptr, jobs[g].out.roots != nullptr));
+    if (!js[g].src_dev) stage_bytes = std::max(stage_bytes, js[g].chunk * js[g].blob_words * 8);
+  }
+  int rc;
+  for (int k = 0; k < depth; k++)
+    if ((rc = ensureWorkspace(ctx, k, ws_bytes))) return rc;
+  if (stage_bytes && (rc = ensureStage(ctx, stage_bytes))) return rc;
+  // ---- outputs that may live on the host (temporaries are allocated in stream order on the primary stream) ---------------
+  for (size_t g = 0; g < jobs.size(); g++) {
+    if (!live(g)) continue;
+    const DevCircuit &d = jobs[g].cir->dev;
+    const Outputs &out = jobs[g].out;
+    JobState &t = js[g];
+    const size_t n = jobs[g].n;
+    if ((rc = t.i_ch.init(ctx, out.challenges_in, (size_t)d.ch_words * n * 8))) return rc;
+    if ((rc = t.o_roots.init(ctx, out.roots, (size_t)4 * (4 + d.nsteps) * n * d.Q * 8))) return rc;
+    if ((rc = t.o_ch.init(ctx, out.challenges, (size_t)d.ch_words * n * 8))) return rc;
+    if ((rc = t.o_comb.init(ctx, out.combined, (size_t)2 * d.r * n * 8))) return rc;
+    if ((rc = t.o_eq.init(ctx, out.eqmask, n))) return rc;
+    if ((rc = t.o_status.init(ctx, out.status, n * 4))) return rc;
+    if ((rc = t.o_bits.init(ctx, out.accept_bits, (n + 31) / 32 * 4))) return rc;
+    if ((rc = t.o_qs.init(ctx, out.qstatus, n * d.Q * 4))) return rc;
+    if ((rc = t.o_folded.init(ctx, out.folded, (size_t)2 * n * d.Q * 8))) return rc;
+  }
+  // Declared after the DevOut temporaries (js), so it is destroyed BEFORE them: any early return below (a failed launch or
   // CUDA call in the chunk loop) first waits for the lanes that were already forked — their kernels may still be writing
   // the temporaries that the DevOut destructors hand back to the pool on the primary stream.
   struct LaneGuard {
@@ -342,48 +384,83 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     lane_guard.armed = true;
     for (int i = 1; i < depth; i++) P2V_CUDA(ctx, cudaStreamWaitEvent(streams[i], ctx->fork_ev, 0));
   }
-  if (!src_dev) lane_guard.armed = true;  // the copy stream runs ahead of the primary one as well
+  if (stage_bytes) lane_guard.armed = true;  // the copy stream runs ahead of the primary one as well
   const bool timed = depth == 1;
-  static const bool no_split = getenv("P2V_NO_SPLIT") != nullptr;  // A/B aid: the Merkle kernel in one launch after K4/K5
+  static const int force_split = getenv("P2V_SPLIT") ? atoi(getenv("P2V_SPLIT")) : -1;
   static const bool trace_on = getenv("P2V_TRACE") != nullptr;
   std::vector<TracePoint> trace;
-  auto mark = [&](const char *what, int chunk_i, size_t m_i, cudaStream_t s) {
+  auto mark = [&](const char *what_, int chunk_i, size_t m_i, cudaStream_t s) {
     if (!trace_on) return;
     cudaEvent_t e;
     cudaEventCreate(&e);
     cudaEventRecord(e, s);
-    trace.push_back({what, chunk_i, m_i, e});
+    trace.push_back({what_, chunk_i, m_i, e});
   };
   double host_setup = host_ms();
   mark("begin", -1, 0, ctx->stream);
-  int k = 0;
-  // Chunk schedule: equal chunks, except for host input with a user-set chunk >= 8192 proofs, which ramps up from
-  // chunk/8 by x9/8 per chunk — the copy of chunk k+1 must not take longer than the kernels of chunk k, and PCIe
-  // delivers proofs only ~1.1x faster than the GPU verifies them (measured with 2 GiB chunks, tools/ramp_sweep.sh:
-  // x2 292k, x1.5 296k, x1.25 300k, x1.125 319k proofs/s).  (A taper of the default 0.5 GiB schedule at both ends —
-  // chunk/4, chunk/2, ..., chunk/2, chunk/4 — measured WORSE: 330k against 368k proofs/s.)
-  std::vector<size_t> sched;
-  {
-    bool ramped = !src_dev && depth >= 2 && chunk >= 8 * 1024;
-    size_t step = ramped ? chunk / P2V_RAMP_START_DIV / 32 * 32 : chunk;
-    for (size_t done = 0; done < n;) {
-      size_t m = std::min(step, n - done);
-      sched.push_back(m);
-      done += m;
-      if (ramped) step = std::min(chunk, (step * P2V_RAMP_NUM / P2V_RAMP_DEN + 31) / 32 * 32);
+  // ---- chunk schedule ----------------------------------------------------------------------------------------------------
+  // Per job: equal chunks, except for host input with a user-set chunk >= 8192 proofs, which ramps up from chunk/8 by x9/8
+  // per chunk — the copy of chunk k+1 must not take longer than the kernels of chunk k (measured with 2 GiB chunks,
+  // tools/ramp_sweep.sh: x2 292k, x1.5 296k, x1.25 300k, x1.125 319k proofs/s).  P2V_TAPER (tuning aid) shortens the chunks at
+  // the ends of the default host schedule.  Jobs follow each other in the order given; their chunks share the lanes.
+  std::vector<Chunk> sched;
+  static const int taper = getenv("P2V_TAPER") ? atoi(getenv("P2V_TAPER")) : 0;
+  for (size_t g = 0; g < jobs.size(); g++) {
+    if (!live(g)) continue;
+    const size_t n = jobs[g].n, chunk = js[g].chunk;
+    const bool src_dev = js[g].src_dev;
+    std::vector<size_t> sizes;
+    if (!src_dev && depth >= 2 && taper && chunk < 8 * 1024 && n > 6 * chunk) {
+      auto r32 = [](size_t v) { return std::max<size_t>(32, v / 32 * 32); };
+      std::vector<size_t> head, tail;
+      if (taper == 1) head = {r32(chunk / 4), r32(chunk / 2)};
+      tail = {r32(chunk / 2), r32(chunk / 4), r32(chunk / 4)};
+      size_t used = 0;
+      for (size_t v : head) used += v;
+      for (size_t v : tail) used += v;
+      for (size_t v : head) sizes.push_back(v);
+      for (size_t done = used; done < n;) {
+        size_t m = std::min(chunk, n - done);
+        sizes.push_back(m);
+        done += m;
+      }
+      for (size_t v : tail) sizes.push_back(v);
+    } else {
+      bool ramped = !src_dev && depth >= 2 && chunk >= 8 * 1024;
+      size_t step = ramped ? chunk / P2V_RAMP_START_DIV / 32 * 32 : chunk;
+      for (size_t done = 0; done < n;) {
+        size_t m = std::min(step, n - done);
+        sizes.push_back(m);
+        done += m;
+        if (ramped) step = std::min(chunk, (step * P2V_RAMP_NUM / P2V_RAMP_DEN + 31) / 32 * 32);
+      }
+    }
+    size_t c0 = 0;
+    for (size_t m : sizes) {
+      sched.push_back({(int)g, c0, m});
+      c0 += m;
     }
   }
-  for (size_t c0 = 0; k < (int)sched.size(); c0 += sched[k], k++) {
-    const size_t m = sched[k];
-    const u64 *src = blobs + c0 * blob_words;
-    int b = k & 1;              // staging buffer (host input): two of them, released by K0
+  int nstaged = 0;  // host-input chunks issued so far: they alternate between the two staging buffers
+  for (int k = 0; k < (int)sched.size(); k++) {
+    const Chunk &ck = sched[k];
+    const Job &job = jobs[ck.job];
+    JobState &t = js[ck.job];
+    const DevCircuit &d = job.cir->dev;
+    const Outputs &out = job.out;
+    const size_t m = ck.m, c0 = ck.c0, n = job.n, blob_words = t.blob_words;
+    const bool src_dev = t.src_dev;
+    const u64 *src = job.blobs + c0 * blob_words;
     int lane = k % depth;       // stream + workspace of this chunk
     cudaStream_t st = streams[lane];
-    Workspace &ws = wsp[lane];
-    ws.ch_in = i_ch.as<u64>(); ws.ch_in_n = n; ws.ch_in_off = c0;
+    Workspace ws;
+    carve(d, m, (char *)(lane == 0 ? ctx->ws : ctx->lane_ws[lane]), &ws, out.folded != nullptr, out.roots != nullptr);
+    ws.ch_in = t.i_ch.as<u64>(); ws.ch_in_n = n; ws.ch_in_off = c0;
+    int b = 0;
     if (!src_dev) {
       // double-buffered staging: the H2D copy of chunk k+1 overlaps the kernels of chunk k; buffer b is free
-      // again once the K0 that read it (chunk k-2) has finished
+      // again once the K0 that read it (two staged chunks ago) has finished
+      b = nstaged++ & 1;
       P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done[b], 0));
       mark("copy_start", k, m, ctx->copy_stream);
       P2V_CUDA(ctx, cudaMemcpyAsync(ctx->stage_buf[b], src, m * blob_words * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -402,8 +479,12 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
     mark("k0_end", k, m, st);
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     // K4 + K5 on the lane's side stream when the Merkle kernel runs in two phases: the leaf phase needs nothing from the
-    // transcript, so the per-proof chains of K4/K5 (latency-bound, ~5 ms per chunk whatever its size) hide beside it
-    const bool split = (what & RUN_FRI) && !no_split;
+    // transcript, so the per-proof chains of K4/K5 (latency-bound, ~5 ms per chunk whatever its size) hide beside it.
+    // Measured at 10^5 proofs (bench.py): host input, 0.5 GiB chunks of 4.2 k proofs, where the ~5 ms chain of K4 is half of a
+    // chunk's Merkle time: 379 k -> 397 k proofs/s end to end with the split; device-resident input, 25 k-proof chunks: the GPU
+    // is saturated either way (the step is already within 2% of the sum of all kernels' work) and the second launch costs 1%
+    // (436 k -> 431 k) — so the split follows the input.  P2V_SPLIT=0/1 forces it (A/B aid).
+    const bool split = (what & RUN_FRI) && (force_split >= 0 ? force_split == 1 : !src_dev);
     cudaStream_t side = (split && depth >= 2) ? ctx->side_stream[lane] : st;
     if (side != st) {
       P2V_CUDA(ctx, cudaEventRecord(ctx->staged_ev[lane], st));
@@ -437,27 +518,30 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
         P2V_MERKLE_LAUNCH(MERKLE_PATH);
       } else {
         P2V_MERKLE_LAUNCH(MERKLE_ALL);
+        if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
       }
 #undef P2V_MERKLE_LAUNCH
       if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
       P2V_LAUNCH_ON(ctx, st, k_fri_query, p2v_grid_for(ctx, m * d.Q, 256, 4), 256, 0, d, ws, m);
+    } else if (side != st) {
+      P2V_CUDA(ctx, cudaStreamWaitEvent(st, ctx->transcript_ev[lane], 0));
     }
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
     // K7
     if (out.verdict_mode) {
-      u32 *stp = o_status.as<u32>() ? o_status.as<u32>() + c0 : nullptr;
-      u32 *bits = o_bits.as<u32>() ? o_bits.as<u32>() + c0 / 32 : nullptr;
+      u32 *stp = t.o_status.as<u32>() ? t.o_status.as<u32>() + c0 : nullptr;
+      u32 *bits = t.o_bits.as<u32>() ? t.o_bits.as<u32>() + c0 / 32 : nullptr;
       P2V_LAUNCH_ON(ctx, st, k_verdict, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m, out.verdict_mode, stp, bits);
     }
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
     mark("chunk_end", k, m, st);
     // optional intermediate outputs
-    if (o_ch.dev) P2V_LAUNCH_ON(ctx, st, k_copy_planes, p2v_grid_for(ctx, m * d.ch_words, 256, 8), 256, 0, ws.ch, m, d.ch_words, o_ch.as<u64>(), n, c0);
-    if (o_comb.dev) P2V_LAUNCH_ON(ctx, st, k_copy_planes, p2v_grid_for(ctx, m * 2 * d.r, 256, 8), 256, 0, ws.comb, m, 2 * d.r, o_comb.as<u64>(), n, c0);
-    if (o_eq.dev) P2V_LAUNCH_ON(ctx, st, k_copy_bytes, p2v_grid_for(ctx, m, 256, 8), 256, 0, ws.eqmask, m, o_eq.as<uint8_t>() + c0);
-    if (o_qs.dev) P2V_LAUNCH_ON(ctx, st, k_copy_qstat, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.qstat, m, d.Q, o_qs.as<u32>(), c0);
-    if (o_roots.dev) P2V_LAUNCH_ON(ctx, st, k_copy_roots, p2v_grid_for(ctx, m * d.Q * 4 * (4 + d.nsteps), 256, 8), 256, 0, ws.roots, m, d.Q, 4 + d.nsteps, o_roots.as<u64>(), n, c0);
-    if (o_folded.dev) P2V_LAUNCH_ON(ctx, st, k_copy_folded, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.folded, m, d.Q, o_folded.as<u64>(), n, c0);
+    if (t.o_ch.dev) P2V_LAUNCH_ON(ctx, st, k_copy_planes, p2v_grid_for(ctx, m * d.ch_words, 256, 8), 256, 0, ws.ch, m, d.ch_words, t.o_ch.as<u64>(), n, c0);
+    if (t.o_comb.dev) P2V_LAUNCH_ON(ctx, st, k_copy_planes, p2v_grid_for(ctx, m * 2 * d.r, 256, 8), 256, 0, ws.comb, m, 2 * d.r, t.o_comb.as<u64>(), n, c0);
+    if (t.o_eq.dev) P2V_LAUNCH_ON(ctx, st, k_copy_bytes, p2v_grid_for(ctx, m, 256, 8), 256, 0, ws.eqmask, m, t.o_eq.as<uint8_t>() + c0);
+    if (t.o_qs.dev) P2V_LAUNCH_ON(ctx, st, k_copy_qstat, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.qstat, m, d.Q, t.o_qs.as<u32>(), c0);
+    if (t.o_roots.dev) P2V_LAUNCH_ON(ctx, st, k_copy_roots, p2v_grid_for(ctx, m * d.Q * 4 * (4 + d.nsteps), 256, 8), 256, 0, ws.roots, m, d.Q, 4 + d.nsteps, t.o_roots.as<u64>(), n, c0);
+    if (t.o_folded.dev) P2V_LAUNCH_ON(ctx, st, k_copy_folded, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.folded, m, d.Q, t.o_folded.as<u64>(), n, c0);
   }
   if (depth >= 2) {
     // join: whoever orders work after us on the primary stream (D2H below, the caller's events, NCCL) sees all lanes
@@ -469,9 +553,13 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   lane_guard.armed = false;  // every lane is joined into the primary stream from here on
   double host_issued = host_ms();
   bool any_host = false;
-  for (DevOut *o : {&o_ch, &o_comb, &o_eq, &o_status, &o_bits, &o_qs, &o_folded, &o_roots}) {
-    if ((rc = o->finish())) return rc;
-    any_host = any_host || (o->host != nullptr);
+  for (size_t g = 0; g < jobs.size(); g++) {
+    if (!live(g)) continue;
+    JobState &t = js[g];
+    for (DevOut *o : {&t.o_ch, &t.o_comb, &t.o_eq, &t.o_status, &t.o_bits, &t.o_qs, &t.o_folded, &t.o_roots}) {
+      if ((rc = o->finish())) return rc;
+      any_host = any_host || (o->host != nullptr);
+    }
   }
   if (any_host) {
     P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -479,18 +567,29 @@ int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t
   if (trace_on) {
     double host_synced = host_ms();
     P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    fprintf(stderr, "[p2v trace] host: setup %.3f ms, all chunks issued %.3f ms, outputs synced %.3f ms (n = %zu, %s input)\n", host_setup,
-            host_issued, host_synced, n, src_dev ? "device" : "host");
-    for (auto &t : trace) {
+    fprintf(stderr, "[p2v trace] host: setup %.3f ms, all chunks issued %.3f ms, outputs synced %.3f ms (%zu jobs, %zu chunks)\n", host_setup,
+            host_issued, host_synced, jobs.size(), sched.size());
+    for (auto &tp : trace) {
       float ms = 0;
-      cudaEventElapsedTime(&ms, trace[0].ev, t.ev);
-      fprintf(stderr, "[p2v trace] %8.3f ms  chunk %3d (%6zu proofs)  %s\n", ms, t.chunk, t.m, t.what);
+      cudaEventElapsedTime(&ms, trace[0].ev, tp.ev);
+      fprintf(stderr, "[p2v trace] %8.3f ms  chunk %3d (%6zu proofs)  %s\n", ms, tp.chunk, tp.m, tp.what);
     }
-    for (auto &t : trace) cudaEventDestroy(t.ev);
+    for (auto &tp : trace) cudaEventDestroy(tp.ev);
   }
   ctx->last_ms.clear();
   if (timed) ctx->last_ms["_pending"] = 1.0f;
-  return P2V_OK;
+  return first_error();
+}
+
+int runBatch(p2v_ctx *ctx, const p2v_circuit *cir, const uint64_t *blobs, size_t n, int what, Outputs out) {
+  if (!ctx || !cir || !blobs) return p2v_fail(ctx, P2V_E_INVALID, "NULL argument");
+  if (n == 0) return P2V_OK;
+  std::vector<Job> jobs(1);
+  jobs[0].cir = cir;
+  jobs[0].blobs = blobs;
+  jobs[0].n = n;
+  jobs[0].out = out;
+  return runJobs(ctx, jobs, what);
 }
 
 }  // namespace
@@ -598,6 +697,10 @@ int p2v_circuit_create(p2v_ctx *ctx, const p2v_shape *shape, const uint64_t *vke
   P2V_CUDA(ctx, cudaMemcpy(c->d_blob, h.data(), words * 8, cudaMemcpyHostToDevice));
   d.vkey = c->d_blob + o_vkey; d.k_is = c->d_blob + o_kis; d.weights = c->d_blob + o_w; d.lut_pairs = c->d_blob + o_lut; d.tab = c->d_blob + o_tab;
   buildTranscript(d);
+  if (d.nops > P2V_MAX_TOPS) {
+    cudaFree(c->d_blob);
+    return p2v_fail(ctx, P2V_E_UNSUPPORTED, "transcript has more than P2V_MAX_TOPS operations");
+  }
   *out = c.release();
   return P2V_OK;
 }
@@ -681,14 +784,22 @@ int p2v_stage(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t 
 }
 
 int p2v_verify_groups(p2v_ctx *ctx, size_t n_groups, const p2v_circuit *const *circuits, const uint64_t *const *blobs,
-                      const size_t *counts, uint32_t *const *accept_bits, uint32_t *const *status) {
+                      const size_t *counts, uint32_t *const *accept_bits, uint32_t *const *status, int32_t *rcs) {
   if (!ctx || (n_groups && (!circuits || !blobs || !counts || !accept_bits))) return p2v_fail(ctx, P2V_E_INVALID, "p2v_verify_groups: NULL argument");
+  std::vector<Job> jobs(n_groups);
   for (size_t g = 0; g < n_groups; g++) {
-    if (counts[g] == 0) continue;
-    int rc = p2v_verify_batch(ctx, circuits[g], blobs[g], counts[g], accept_bits[g], status ? status[g] : nullptr);
-    if (rc != P2V_OK) return rc;
+    jobs[g].cir = circuits[g];
+    jobs[g].blobs = blobs[g];
+    jobs[g].n = counts[g];
+    jobs[g].out.status = status ? status[g] : nullptr;
+    jobs[g].out.accept_bits = accept_bits[g];
+    jobs[g].out.verdict_mode = 3;
+    if (counts[g] && !accept_bits[g]) { jobs[g].rc = P2V_E_INVALID; jobs[g].err = "p2v_verify_groups: accept_bits of a non-empty group is NULL"; }
   }
-  return P2V_OK;
+  int rc = runJobs(ctx, jobs, RUN_CHALLENGES | RUN_CONSTRAINTS | RUN_FRI);
+  if (rcs)
+    for (size_t g = 0; g < n_groups; g++) rcs[g] = jobs[g].rc;
+  return rc;
 }
 
 int p2v_synth_batch(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *template_blob, size_t n, const int32_t *tamper_word,

@@ -12,7 +12,7 @@
 #include "../../include/p2v.h"
 
 #define P2V_MAX_CHALLENGES 4
-#define P2V_MAX_TOPS 48
+#define P2V_MAX_TOPS 64
 
 // One operation of the transcript (Challenge/Verifier.hs:73-94, Challenge/FRI.hs:73-97)
 enum { TOP_ABSORB_PROOF = 0, TOP_ABSORB_VKEY = 1, TOP_ABSORB_PIH = 2, TOP_SPONGE_FINISH = 3, TOP_SQUEEZE = 4 };

@@ -176,14 +176,40 @@ def test_json_in_verdict_out(p2v, ctx, orc):
 
 
 def test_heterogeneous_groups(p2v, ctx, orc):
-    """Proofs of different circuits (other degree_bits, gate sets, reduction strategies, lookups) in one call."""
+    """Proofs of different circuits (other degree_bits, gate sets, reduction strategies, lookups) in one call: the chunks of
+    all groups share the pipeline lanes; ten groups (some tiny, one empty) against the oracle."""
     groups, wants = [], []
-    for name, n in (("small6", 40), ("fixed4", 33), ("reallu6", 21), ("real5", 17)):
+    plan = (("small6", 40), ("fixed4", 33), ("reallu6", 21), ("real5", 17), ("arity5", 5), ("mid5", 1), ("lookup6", 64),
+            ("small6", 0), ("real5", 3), ("fixed4", 96))
+    for name, n in plan:
         cir, shape, lay, vkey, blob = _circuit(p2v, ctx, name)
-        blobs, words, deltas = fixtures.tampered_batch(blob, lay, shape, n, seed=5)
+        blobs, words, deltas = fixtures.tampered_batch(blob, lay, shape, max(n, 1), seed=5)
+        blobs = blobs[:n]
         groups.append((cir, blobs))
-        wants.append(orc.verify_batch(shape, vkey, blobs, threads=4, fast=True)["status"])
-    got = p2v.verify_groups(ctx, groups)
-    for (acc, status), want in zip(got, wants):
-        assert np.array_equal(status, want)
-        assert np.array_equal(acc, want == 0)
+        wants.append(orc.verify_batch(shape, vkey, blobs, threads=4, fast=True)["status"] if n else np.zeros(0, dtype=np.uint32))
+    for depth in (p2v.DEFAULT_PIPELINE, 1):
+        ctx.set_pipeline(depth)
+        got = p2v.verify_groups(ctx, groups)
+        for (acc, status), want in zip(got, wants):
+            assert np.array_equal(status, want)
+            assert np.array_equal(acc, want == 0)
+    ctx.set_pipeline(p2v.DEFAULT_PIPELINE)
+
+
+def test_a_group_that_cannot_run_does_not_stop_the_others(p2v, ctx, orc):
+    """p2v_verify_groups keeps going past a bad group and reports per-group codes."""
+    cir, shape, lay, vkey, blob = _circuit(p2v, ctx, "small6")
+    other = p2v.Context(0)
+    try:
+        foreign = p2v.Circuit(other, shape, vkey)  # belongs to another context: invalid in this call
+        blobs, _, _ = fixtures.tampered_batch(blob, lay, shape, 20, seed=8)
+        want = orc.verify_batch(shape, vkey, blobs, threads=4, fast=True)["status"]
+        out, rcs = p2v.verify_groups(ctx, [(cir, blobs), (foreign, blobs), (cir, blobs[:7])], return_codes=True)
+        assert list(rcs) == [0, -1, 0]
+        assert np.array_equal(out[0][1], want) and np.array_equal(out[2][1], want[:7])
+        assert not out[1][0].any()
+        with pytest.raises(p2v.P2VError):
+            p2v.verify_groups(ctx, [(cir, blobs), (foreign, blobs)])
+        foreign.close()
+    finally:
+        other.close()

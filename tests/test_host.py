@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(p2v):
     for sym in sorted(declared):
         assert hasattr(lib, sym), "libp2v.so does not export %s" % sym
     assert declared == set(p2v.EXPORTED_SYMBOLS)
-    assert p2v.lib().p2v_abi_version() == 1
+    assert p2v.lib().p2v_abi_version() == 2
 
 
 def test_no_cpu_fallback(p2v):
