@@ -232,6 +232,8 @@ def main():
                     help="template proof of the batch: real12 (default) = standard recursion configuration with an active gate on every row "
                          "(4 selector groups); s12 = same shape, Plonky2's own 3-group selector layout, all-Noop rows")
     ap.add_argument("--parity-proofs", type=int, default=32808, help="size of the untimed same-batch sharded check at world > 1 (0 = skip)")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
+                    help="how p2v_verify_batch_sharded gathers the bitmap at world > 1: ncclAllGather (default) or direct stores into the peers' buffers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="proofs per staged chunk on the host-buffer path (0 = library default)")
     args = ap.parse_args()
@@ -275,6 +277,8 @@ def main():
     if world > 1:
         n = max(32, n // 32 * 32)  # equal slices of the weak-scaling batch are exactly the ranks' batches
         sharding.init_comm(ctx, dist)  # libp2v's own NCCL communicator; torch ships the 128-byte id
+        if args.gather == "peer":
+            ctx.peer_enable()
     n_total = n * world
     W = lay.blob_words
     stream = torch.cuda.ExternalStream(ctx.stream)
@@ -473,8 +477,9 @@ def main():
                    "verdict_histogram": hist,
                    "host_placement": placement,
                    "pipeline": "4 lanes (stream + workspace); chunks of 3 GiB (device-resident input) / 0.5 GiB (host input); K0/K4/K5 of the next chunks overlap K6 of the current one",
-                   "multi_gpu": ("contiguous slices, one C-ABI call per step: p2v_verify_batch_sharded = verify + ncclAllGather of the accept bitmap "
-                                 "(libp2v's own communicator, NCCL %s)" % (ctx.nccl_info()[2],)) if world > 1 else "single GPU"},
+                   "multi_gpu": ("contiguous slices, one C-ABI call per step: p2v_verify_batch_sharded = verify + %s of the accept bitmap "
+                                 "(libp2v's own communicator, NCCL %s)" % ("ncclAllGather" if args.gather == "nccl" else "peer-store gather (direct NVLink stores + flags)",
+                                                                            ctx.nccl_info()[2])) if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_e2e * W * 8, "d2h_bytes_per_step": int(h_bits.nbytes + h_status.nbytes),
                 "proofs_per_gpu": n_e2e, "h2d_copy_gbs_measured": alone[len(alone) // 2],
                 "h2d_copy_gbs_per_rank_alone": {"min": alone[0], "median": alone[len(alone) // 2], "max": alone[-1]},

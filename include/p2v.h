@@ -327,6 +327,14 @@ int p2v_nccl_info(p2v_ctx *ctx, int *rank, int *world, int *nccl_version);
 int p2v_verify_batch_sharded(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs_local, size_t n_total, int rank,
                              int world, uint32_t *accept_bits_full, uint32_t *status_local);
 
+/* Opt-in B200-native form of the gather (collective; needs the communicator once, for the handle exchange): every rank
+ * exports a small gather buffer with cudaIpc, and from then on p2v_verify_batch_sharded publishes its slice with direct
+ * stores into every peer's buffer over NVLink/NVSwitch plus a system-scope release flag, and waits for the peers' flags —
+ * no NCCL kernel on the path.  All ranks on one node with peer access; at most 16 ranks and 2^18 bitmap words per call
+ * (larger calls fall back to ncclAllGather).  Results are identical (tests/sharded_worker.py). */
+int p2v_peer_enable(p2v_ctx *ctx);
+int p2v_peer_disable(p2v_ctx *ctx);
+
 /* K0 alone: AoS blobs [n][blob_words] -> structure-of-arrays word planes, the layout every kernel reads
  * (replaces the Haskell lists of Types.hs:251-279).  planes_out (device or host): [blob_words][n] with plane order
  * pp[w] for w < proof_words, then qp[wq * num_queries + q] for wq < query_words. */

@@ -156,6 +156,8 @@ def lib():
         "p2v_nccl_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "p2v_verify_batch_sharded": (C.c_int, [vp, vp, u64p, sz, C.c_int, C.c_int, u32p, u32p]),
         "p2v_stage": (C.c_int, [vp, vp, u64p, sz, u64p]),
+        "p2v_peer_enable": (C.c_int, [vp]),
+        "p2v_peer_disable": (C.c_int, [vp]),
         "p2v_verify_intermediates": (C.c_int, [vp, vp, u64p, sz, C.POINTER(Intermediates)]),
         "p2v_debug_field_op": (C.c_int, [vp, C.c_int, u64p, u64p, u64p, sz]),
         "p2v_int_pipe_peak": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double)]),
@@ -178,6 +180,7 @@ EXPORTED_SYMBOLS = [
     "p2v_fri", "p2v_verify_batch", "p2v_verify_groups", "p2v_ctx_set_chunk", "p2v_ctx_set_pipeline", "p2v_synth_batch", "p2v_int_pipe_peak", "p2v_ctx_last_ms",
     "p2v_shard_slice_len", "p2v_shard_bounds", "p2v_nccl_unique_id", "p2v_nccl_init", "p2v_nccl_attach", "p2v_nccl_finalize",
     "p2v_nccl_info", "p2v_verify_batch_sharded", "p2v_stage", "p2v_verify_intermediates", "p2v_debug_field_op",
+    "p2v_peer_enable", "p2v_peer_disable",
 ]
 
 
@@ -359,6 +362,13 @@ class Context:
         r, w, v = C.c_int(), C.c_int(), C.c_int()
         self._check(lib().p2v_nccl_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
         return r.value, w.value, v.value
+
+    def peer_enable(self):
+        """Collective: gather the bitmap with direct peer stores + flags instead of ncclAllGather (p2v_peer_enable)."""
+        self._check(lib().p2v_peer_enable(self._h))
+
+    def peer_disable(self):
+        self._check(lib().p2v_peer_disable(self._h))
 
     def nccl_finalize(self):
         self._check(lib().p2v_nccl_finalize(self._h))

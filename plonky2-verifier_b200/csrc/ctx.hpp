@@ -46,6 +46,7 @@ struct p2v_ctx {
   void *nccl_comm = nullptr;   // ncclComm_t
   bool nccl_owned = false;     // created by p2v_nccl_init (destroyed with the context) or attached by the caller
   int nccl_rank = 0, nccl_world = 1;
+  void *peer = nullptr;        // p2v_peer_state (sharded_api.cu): peer-mapped gather buffers, opt-in
 };
 
 extern thread_local std::string p2v_tls_error;

@@ -58,11 +58,27 @@ def main():
                 assert not allbits[r * per + (b - a):(r + 1) * per].any(), "padding bits set"
                 assert np.array_equal(allbits[r * per: r * per + (b - a)], want[a:b] == 0), "rank %d's slice is not at words [%d, %d)" % (r, r * per // 32, (r + 1) * per // 32)
         cir.close()
+    # ---- the gather without NCCL: direct stores into the peers' buffers + flags (p2v_peer_enable) ----
+    ctx.peer_enable()
+    shape, lay, vkey, blob = fixtures.load("small6")
+    cir = p2v.Circuit(ctx, shape, vkey)
+    for rep, n_total in enumerate((100, 33, 64, 100, 7, 256, 100)):  # several epochs back to back: both halves of the buffers
+        blobs, _, _ = fixtures.tampered_batch(blob, lay, shape, n_total, seed=100 + rep)
+        want = orc.verify_batch(shape, vkey, blobs, threads=8, fast=True)["status"]
+        start, stop = p2v.shard_bounds(n_total, rank, world)
+        acc, st = cir.verifyProofSharded(blobs[start:stop], n_total, rank, world)
+        assert np.array_equal(acc, want == 0), ("peer gather", n_total, rank)
+        assert np.array_equal(st, want[start:stop])
+        d_local = torch.from_numpy(blobs[start:stop].view(np.int64).copy()).cuda()
+        full, _ = sharding.verify_batch_sharded(cir, d_local, n_total, rank, world, dist)
+        assert np.array_equal(p2v.unpack_bits(full.cpu().numpy().view(np.uint32), n_total), want == 0), ("peer gather, device buffers", n_total, rank)
+    cir.close()
+    ctx.peer_disable()
     r_, w_, ver = ctx.nccl_info()
     assert (r_, w_) == (rank, world) and ver > 0
     dist.barrier()
     if rank == 0:
-        print("SHARDED_OK world=%d nccl=%d" % (world, ver))
+        print("SHARDED_OK world=%d nccl=%d (NCCL all-gather and peer-store gather)" % (world, ver))
     dist.destroy_process_group()
 
 
