@@ -33,10 +33,11 @@ struct p2v_ctx {
   // verify workspace (lazily grown)
   void *ws = nullptr;
   size_t ws_bytes = 0;
-  void *stage_buf[2] = {nullptr, nullptr};
+  void *stage_buf[P2V_MAX_DEPTH + 1] = {};  // ring of AoS chunk buffers for host input (depth + 1 in use)
   size_t stage_bytes = 0;
+  int stage_count = 0;
+  cudaEvent_t stage_filled[P2V_MAX_DEPTH + 1] = {}, stage_free[P2V_MAX_DEPTH + 1] = {};
   cudaEvent_t ev[8] = {};
-  cudaEvent_t copy_done[2] = {}, compute_done[2] = {};
   // Private stream-ordered pool for the staged copies of host inputs/outputs (DevIn/DevOut).  Its release
   // threshold is unlimited: with the default pool (threshold 0) every synchronisation hands the freed blocks
   // back to the driver and the next call re-maps them, which cost 30-160 ms of host time per call at random

@@ -19,9 +19,9 @@ static int ctxInit(p2v_ctx *ctx, int device) {
   }
   P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
   for (auto &ev : ctx->ev) P2V_CUDA(nullptr, cudaEventCreate(&ev));
-  for (int i = 0; i < 2; i++) {
-    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming));
-    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->compute_done[i], cudaEventDisableTiming));
+  for (int i = 0; i < P2V_MAX_DEPTH + 1; i++) {
+    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->stage_filled[i], cudaEventDisableTiming));
+    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->stage_free[i], cudaEventDisableTiming));
   }
   cudaMemPoolProps props = {};
   props.allocType = cudaMemAllocationTypePinned;
@@ -93,9 +93,9 @@ void p2v_ctx_destroy(p2v_ctx *ctx) {
     if (b) cudaFree(b);
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
-  for (int i = 0; i < 2; i++) {
-    if (ctx->copy_done[i]) cudaEventDestroy(ctx->copy_done[i]);
-    if (ctx->compute_done[i]) cudaEventDestroy(ctx->compute_done[i]);
+  for (int i = 0; i < P2V_MAX_DEPTH + 1; i++) {
+    if (ctx->stage_filled[i]) cudaEventDestroy(ctx->stage_filled[i]);
+    if (ctx->stage_free[i]) cudaEventDestroy(ctx->stage_free[i]);
   }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

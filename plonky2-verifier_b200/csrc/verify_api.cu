@@ -132,7 +132,6 @@ size_t carve(const DevCircuit &d, size_t m, char *base, Workspace *ws, bool want
     return base ? base + o : (char *)nullptr;
   };
   u64 *pp = (u64 *)take((size_t)d.L.proof_words * m * 8);
-  u64 *qp = (u64 *)take((size_t)d.L.query_words * d.Q * m * 8);
   u64 *ch = (u64 *)take((size_t)d.ch_words * m * 8);
   u64 *pih = (u64 *)take(4 * m * 8);
   u64 *pre = (u64 *)take(4 * m * 8);
@@ -146,7 +145,7 @@ size_t carve(const DevCircuit &d, size_t m, char *base, Workspace *ws, bool want
   u64 *roots = want_roots ? (u64 *)take((size_t)4 * (4 + d.nsteps) * d.Q * m * 8) : nullptr;
   if (ws) {
     ws->roots = roots; ws->ch_in = nullptr; ws->ch_in_n = 0; ws->ch_in_off = 0;
-    ws->pp = pp; ws->qp = qp; ws->ch = ch; ws->pih = pih; ws->pre = pre; ws->apow = apow; ws->comb = comb; ws->qstat = qstat;
+    ws->pp = pp; ws->aos = nullptr; ws->ch = ch; ws->pih = pih; ws->pre = pre; ws->apow = apow; ws->comb = comb; ws->qstat = qstat;
     ws->folded = folded; ws->eqmask = eq; ws->tree_ok = tree_ok; ws->leafdig = leafdig;
   }
   return off;
@@ -174,23 +173,30 @@ int ensureWorkspace(p2v_ctx *ctx, int which, size_t bytes) {
   return P2V_OK;
 }
 
-int ensureStage(p2v_ctx *ctx, size_t bytes) {
-  if (ctx->stage_bytes >= bytes) return P2V_OK;
+// Host input: a ring of `count` device buffers receives the chunks as they are (AoS); the kernels read the query parts in
+// place, so a buffer is free again when the LAST kernel of its chunk has finished (ctx->stage_free[b]).
+int ensureStage(p2v_ctx *ctx, size_t bytes, int count) {
+  if (ctx->stage_bytes >= bytes && ctx->stage_count >= count) return P2V_OK;
   P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   P2V_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  for (int i = 1; i < P2V_MAX_DEPTH; i++) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->lane_stream[i]));
   for (auto &b : ctx->stage_buf) {
     if (b) cudaFree(b);
     b = nullptr;
   }
+  bytes = std::max(bytes, ctx->stage_bytes);
+  count = std::max(count, ctx->stage_count);
   ctx->stage_bytes = 0;
-  for (auto &b : ctx->stage_buf) {
-    cudaError_t e = cudaMalloc(&b, bytes);
+  ctx->stage_count = 0;
+  for (int i = 0; i < count; i++) {
+    cudaError_t e = cudaMalloc(&ctx->stage_buf[i], bytes);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      return p2v_fail(ctx, P2V_E_NOMEM, std::string("staging buffer allocation failed: ") + cudaGetErrorString(e));
+      return p2v_fail(ctx, P2V_E_NOMEM, std::string("staging buffer allocation failed: ") + cudaGetErrorString(e) + " (lower the chunk with p2v_ctx_set_chunk)");
     }
   }
   ctx->stage_bytes = bytes;
+  ctx->stage_count = count;
   return P2V_OK;
 }
 
@@ -342,7 +348,8 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
   int rc;
   for (int k = 0; k < depth; k++)
     if ((rc = ensureWorkspace(ctx, k, ws_bytes))) return rc;
-  if (stage_bytes && (rc = ensureStage(ctx, stage_bytes))) return rc;
+  const int nstage_bufs = depth + 1;  // one per lane in flight + one being filled
+  if (stage_bytes && (rc = ensureStage(ctx, stage_bytes, nstage_bufs))) return rc;
   // ---- outputs that may live on the host (temporaries are allocated in stream order on the primary stream) ---------------
   for (size_t g = 0; g < jobs.size(); g++) {
     if (!live(g)) continue;
@@ -456,26 +463,28 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
     Workspace ws;
     carve(d, m, (char *)(lane == 0 ? ctx->ws : ctx->lane_ws[lane]), &ws, out.folded != nullptr, out.roots != nullptr);
     ws.ch_in = t.i_ch.as<u64>(); ws.ch_in_n = n; ws.ch_in_off = c0;
-    int b = 0;
+    int b = -1;
     if (!src_dev) {
-      // double-buffered staging: the H2D copy of chunk k+1 overlaps the kernels of chunk k; buffer b is free
-      // again once the K0 that read it (two staged chunks ago) has finished
-      b = nstaged++ & 1;
-      P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done[b], 0));
+      // staging ring: the H2D copy of the next chunks overlaps the kernels of the current ones; buffer b is free again
+      // once the last kernel that reads it (the chunk that used it depth + 1 staged chunks ago) has finished
+      b = nstaged++ % nstage_bufs;
+      P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[b], 0));
       mark("copy_start", k, m, ctx->copy_stream);
       P2V_CUDA(ctx, cudaMemcpyAsync(ctx->stage_buf[b], src, m * blob_words * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-      P2V_CUDA(ctx, cudaEventRecord(ctx->copy_done[b], ctx->copy_stream));
+      P2V_CUDA(ctx, cudaEventRecord(ctx->stage_filled[b], ctx->copy_stream));
       mark("copy_end", k, m, ctx->copy_stream);
-      P2V_CUDA(ctx, cudaStreamWaitEvent(st, ctx->copy_done[b], 0));
+      P2V_CUDA(ctx, cudaStreamWaitEvent(st, ctx->stage_filled[b], 0));
       src = (const u64 *)ctx->stage_buf[b];
     }
+    ws.aos = src;
     // K0
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     {
-      dim3 grid((unsigned)((m + 31) / 32), (unsigned)((blob_words + 31) / 32));
-      P2V_LAUNCH_ON(ctx, st, k_stage_transpose, grid, 256, 0, src, m, (int)blob_words, d.L.proof_words, d.L.query_words, d.Q, ws.pp, ws.qp);
+      // only the per-proof part is transposed; the query parts are read in place
+      dim3 grid((unsigned)((m + 31) / 32), (unsigned)((d.L.proof_words + 31) / 32));
+      P2V_LAUNCH_ON(ctx, st, k_stage_transpose, grid, 256, 0, src, m, (int)blob_words, d.L.proof_words, d.L.query_words, d.Q, ws.pp, (u64 *)nullptr,
+                    d.L.proof_words);
     }
-    if (!src_dev) P2V_CUDA(ctx, cudaEventRecord(ctx->compute_done[b], st));
     mark("k0_end", k, m, st);
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     // K4 + K5 on the lane's side stream when the Merkle kernel runs in two phases: the leaf phase needs nothing from the
@@ -534,6 +543,7 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
       P2V_LAUNCH_ON(ctx, st, k_verdict, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m, out.verdict_mode, stp, bits);
     }
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
+    if (b >= 0) P2V_CUDA(ctx, cudaEventRecord(ctx->stage_free[b], st));  // K6a/K6b were the last readers of the chunk's blobs
     mark("chunk_end", k, m, st);
     // optional intermediate outputs
     if (t.o_ch.dev) P2V_LAUNCH_ON(ctx, st, k_copy_planes, p2v_grid_for(ctx, m * d.ch_words, 256, 8), 256, 0, ws.ch, m, d.ch_words, t.o_ch.as<u64>(), n, c0);
@@ -777,7 +787,7 @@ int p2v_stage(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t *blobs, size_t 
   if ((rc = out.init(ctx, planes_out, n * bw * 8))) return rc;
   dim3 grid((unsigned)((n + 31) / 32), (unsigned)((bw + 31) / 32));
   u64 *pp = out.as<u64>();
-  P2V_LAUNCH(ctx, k_stage_transpose, grid, 256, 0, in.as<u64>(), n, (int)bw, d.L.proof_words, d.L.query_words, d.Q, pp, pp + (size_t)d.L.proof_words * n);
+  P2V_LAUNCH(ctx, k_stage_transpose, grid, 256, 0, in.as<u64>(), n, (int)bw, d.L.proof_words, d.L.query_words, d.Q, pp, pp + (size_t)d.L.proof_words * n, (int)bw);
   if ((rc = out.finish())) return rc;
   if (out.host) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return P2V_OK;

@@ -1,11 +1,13 @@
 // K0 (stage/transpose), K4 (Fiat-Shamir challenger), K6 (FRI query rounds), K7 (verdict).
 //
 // Data layout in HBM (DESIGN.md "data layout"): a chunk of n proofs arrives as AoS blobs
-// [n][blob_words] (include/p2v.h p2v_layout) and is transposed ONCE by K0 into word planes:
-//   pp[w][n]                 w < proof_words          per-proof part
-//   qp[(w*Q + q)][n]         w < query_words, q < Q   per-query part
-// so that thread t = (q, proof) of every later kernel reads plane[...][proof]: a warp touches 256
-// contiguous bytes per word.  All kernels are shape-generic: the shape lives in a DevCircuit
+// [n][blob_words] (include/p2v.h p2v_layout).  K0 transposes the PER-PROOF part (5.5% of a blob at S12) into word planes
+//   pp[w][n]                 w < proof_words
+// so that the one-thread-per-proof kernels (K4, K5, the tails of K6a/K6b) read plane[w][proof]: a warp touches 256
+// contiguous bytes per word.  The PER-QUERY parts stay where they are (round 2): a thread (q, proof) of K6a/K6b consumes
+// its OWN contiguous words — 8 per sponge block, 4 per sibling, the whole leaf in combineInitial — so every 32-byte sector
+// it touches is used completely whether or not the warp's addresses are adjacent, and the 12 GB transposed copy of round 1
+// (written once, read once, 1.0x the batch in workspace) bought nothing.  p2v_stage still produces the full plane layout.  All kernels are shape-generic: the shape lives in a DevCircuit
 // passed by value (kernel parameter space, read through the constant cache).
 #pragma once
 #include "poseidon.cuh"
@@ -56,7 +58,7 @@ struct DevCircuit {
 // Per-chunk workspace planes
 struct Workspace {
   u64 *pp;     // [proof_words][n]
-  u64 *qp;     // [query_words*Q][n]
+  const u64 *aos;  // the chunk's blobs as they arrived, [n][blob_words]: the query parts are read in place
   u64 *ch;     // [ch_words][n]   challenges (canonical)
   u64 *pih;    // [4][n]          sponge(public_inputs)
   u64 *pre;    // [4][n]          precomputed reduced openings Y0, Y1 (Plonk/FRI.hs:128-134)
@@ -100,8 +102,10 @@ struct DotAcc {
 // ---- K0: AoS blobs -> SoA planes -----------------------------------------------------------------
 // 32x32 tiles through shared memory: reads are coalesced along the blob (256 B per proof row),
 // writes are coalesced along the proof index (256 B per word plane).
+// `words` = how many leading words of every blob are transposed: proof_words inside the verifier (qp unused), blob_words for
+// p2v_stage.
 __global__ void __launch_bounds__(256) k_stage_transpose(const u64 *__restrict__ blobs, size_t n, int blob_words, int proof_words,
-                                                         int query_words, int Q, u64 *__restrict__ pp, u64 *__restrict__ qp) {
+                                                         int query_words, int Q, u64 *__restrict__ pp, u64 *__restrict__ qp, int words) {
   __shared__ u64 tile[32][33];
   int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   // proof tiles run along grid.x (up to 2^31-1 blocks): grid.y is limited to 65535, i.e. ~2.09 M proofs per chunk
@@ -111,14 +115,14 @@ __global__ void __launch_bounds__(256) k_stage_transpose(const u64 *__restrict__
   for (int k = 0; k < 4; k++) {
     size_t p = p0 + ty + 8 * k;
     int w = w0 + tx;
-    if (p < n && w < blob_words) tile[ty + 8 * k][tx] = blobs[p * (size_t)blob_words + w];
+    if (p < n && w < words) tile[ty + 8 * k][tx] = blobs[p * (size_t)blob_words + w];
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     int w = w0 + ty + 8 * k;
     size_t p = p0 + tx;
-    if (p < n && w < blob_words) {
+    if (p < n && w < words) {
       u64 v = tile[tx][ty + 8 * k];
       if (w < proof_words) {
         pp[(size_t)w * n + p] = v;
@@ -316,15 +320,14 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) k_fri_merkle(const __grid_co
   const size_t total = per_tree * (size_t)(4 + c.nsteps);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const u64 *__restrict__ pp = ws.pp;
-  const u64 *__restrict__ qp = ws.qp;
   const p2v_layout &L = c.L;
-  const size_t qstride = per_tree;  // word w of (q, proof) at qp[w*Q*n + q*n + proof]
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
     int tr = (int)(t / per_tree);
     size_t rem = t - (size_t)tr * per_tree;  // = q*n + proof
     int q = (int)(rem / n);
     size_t p = rem - (size_t)q * n;
-    const u64 *__restrict__ qbase = qp + rem;
+    // query part q of proof p, read in place: word w at qbase[w]
+    const u64 *__restrict__ qbase = ws.aos + p * (size_t)L.blob_words + L.proof_words + (size_t)q * L.query_words;
     u32 index = PHASE == MERKLE_LEAF ? 0u : (u32)ws.ch[(size_t)(c.ch_idx + q) * n + p];  // the leaf phase must not touch K4's output
     int leaf_off, width, sib_off, plen, cap_off;
     if (tr < 4) {
@@ -351,18 +354,18 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) k_fri_merkle(const __grid_co
       if (PHASE != MERKLE_PATH && (PHASE == MERKLE_LEAF || it < nblk)) {
         // sponge block, Hash/Sponge.hs:26-31 (overwrite the first k lanes)
         int k = width - it * 8;
-        const u64 *src = qbase + (size_t)(leaf_off + it * 8) * qstride;
+        const u64 *src = qbase + (leaf_off + it * 8);
 #pragma unroll
         for (int i = 0; i < 8; i++)
-          if (i < k) s[i] = src[(size_t)i * qstride];
+          if (i < k) s[i] = src[i];
       } else {
         // compress with the sibling, Hash/Merkle.hs:30-37
-        const u64 *src = qbase + (size_t)(sib_off + (it - nblk) * 4) * qstride;
+        const u64 *src = qbase + (sib_off + (it - nblk) * 4);
         bool even = (index & 1u) == 0;
         index >>= 1;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          u64 sib = src[(size_t)i * qstride];
+          u64 sib = src[i];
           u64 node = s[i];
           s[i] = even ? node : sib;
           s[4 + i] = even ? sib : node;
@@ -400,14 +403,12 @@ __global__ void __launch_bounds__(256) k_fri_query(const __grid_constant__ DevCi
   size_t total = n * (size_t)c.Q;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   const u64 *__restrict__ pp = ws.pp;
-  const u64 *__restrict__ qp = ws.qp;
   const p2v_layout &L = c.L;
-  const int Q = c.Q;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
     int q = (int)(t / n);
     size_t p = t - (size_t)q * n;
-    const u64 *__restrict__ qbase = qp + (size_t)q * n + p;  // word w of this query at qbase[w*Q*n]
-    const size_t qstride = (size_t)Q * n;
+    // query part q of proof p, read in place (word w at qbase[w]): a thread streams its own leaf values
+    const u64 *__restrict__ qbase = ws.aos + p * (size_t)L.blob_words + L.proof_words + (size_t)q * L.query_words;
     u32 idx = (u32)ws.ch[(size_t)(c.ch_idx + q) * n + p];
     u32 init_bad = 0, step_bad = 0;
 #pragma unroll 1
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(256) k_fri_query(const __grid_constant__ DevCi
       for (int sg = 0; sg < 5; sg++) {
 #pragma unroll 2
         for (int i = 0; i < seg_n[sg]; i++, k++) {
-          u64 x = qbase[(size_t)(seg_off[sg] + i) * qstride];
+          u64 x = qbase[seg_off[sg] + i];
           re.mac(apw[(size_t)(2 * k) * n], x);
           im.mac(apw[(size_t)(2 * k + 1) * n], x);
         }
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(256) k_fri_query(const __grid_constant__ DevCi
       for (int sg = 0; sg < 2; sg++) {
 #pragma unroll 1
         for (int i = 0; i < seg_n[sg]; i++, k++) {
-          u64 x = qbase[(size_t)(seg_off[sg] + i) * qstride];
+          u64 x = qbase[seg_off[sg] + i];
           re.mac(apw[(size_t)(2 * k) * n], x);
           im.mac(apw[(size_t)(2 * k + 1) * n], x);
         }
@@ -493,10 +494,10 @@ __global__ void __launch_bounds__(256) k_fri_query(const __grid_constant__ DevCi
     for (int st = 0; st < c.nsteps; st++) {
       int a = c.arity_bits[st], A = 1 << a;
       int bits = c.lde_bits - c.cum_bits[st];
-      const u64 *ev = qbase + (size_t)L.q_off_step_evals[st] * qstride;
+      const u64 *ev = qbase + L.q_off_step_evals[st];
       // evals !! (idx mod arity) == upstream eval  (:317)
       u32 pos = qidx & (u32)(A - 1);
-      gl2 opened = gl2_make(ev[(size_t)(2 * pos) * qstride], ev[(size_t)(2 * pos + 1) * qstride]);
+      gl2 opened = gl2_make(ev[2 * pos], ev[2 * pos + 1]);
       if (!gl2_eq(opened, eval)) eval_bad |= 1u << st;
       // coset offset ofs = shift * eta_big^rev(bigLog2, (idx>>a)<<a); here its inverse, from the
       // inverse tables: shift = g^(2^cum), eta_big = eta^(2^cum)   (prepareCoset :248-259)
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(256) k_fri_query(const __grid_constant__ DevCi
       gl2 acc = gl2_make(0, 0);
 #pragma unroll 1
       for (int i = 0; i < A; i++) {
-        gl2 cur = gl2_make(ev[(size_t)(2 * i) * qstride], ev[(size_t)(2 * i + 1) * qstride]);
+        gl2 cur = gl2_make(ev[2 * i], ev[2 * i + 1]);
         u32 ix = (u32)i;
         int lvl = 0;
         while (ix & 1u) {
