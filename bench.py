@@ -450,7 +450,9 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "measured" if "hbm_gbs" in peaks else "fallback"
-    algo_bytes = n * W * 8 * 2 + n * W * 8  # K0 reads AoS + writes SoA, later kernels read the planes once
+    # every blob byte is read once by its consumer (query parts in place, K6a + K6b share L2 only by luck: counted twice for
+    # the leaves K6b re-reads) + the per-proof part once more through K0's transposed planes (read + write + read)
+    algo_bytes = n * W * 8 + n * shape.num_queries * sum(lay.oracle_width[o] for o in range(4)) * 8 + 3 * n * lay.proof_words * 8
     hbm_achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic(n)
 

@@ -408,31 +408,18 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
   // ---- chunk schedule ----------------------------------------------------------------------------------------------------
   // Per job: equal chunks, except for host input with a user-set chunk >= 8192 proofs, which ramps up from chunk/8 by x9/8
   // per chunk — the copy of chunk k+1 must not take longer than the kernels of chunk k (measured with 2 GiB chunks,
-  // tools/ramp_sweep.sh: x2 292k, x1.5 296k, x1.25 300k, x1.125 319k proofs/s).  P2V_TAPER (tuning aid) shortens the chunks at
-  // the ends of the default host schedule.  Jobs follow each other in the order given; their chunks share the lanes.
+  // tools/ramp_sweep.sh: x2 292k, x1.5 296k, x1.25 300k, x1.125 319k proofs/s).  Round 2 tried geometric ramps up to 4 k / 8 k /
+  // 16 k / 24 k-proof chunks mirrored at the end, and shorter chunks at the ends of the default schedule: 250 / 258 / 270 / 272 ms
+  // against 250 ms for constant 0.5 GiB chunks (the copies run back to back either way; what is left
+  // is the work in flight when the last copy ends, about three chunks whatever their size).  Jobs follow each other in the
+  // order given; their chunks share the lanes.
   std::vector<Chunk> sched;
-  static const int taper = getenv("P2V_TAPER") ? atoi(getenv("P2V_TAPER")) : 0;
   for (size_t g = 0; g < jobs.size(); g++) {
     if (!live(g)) continue;
     const size_t n = jobs[g].n, chunk = js[g].chunk;
     const bool src_dev = js[g].src_dev;
     std::vector<size_t> sizes;
-    if (!src_dev && depth >= 2 && taper && chunk < 8 * 1024 && n > 6 * chunk) {
-      auto r32 = [](size_t v) { return std::max<size_t>(32, v / 32 * 32); };
-      std::vector<size_t> head, tail;
-      if (taper == 1) head = {r32(chunk / 4), r32(chunk / 2)};
-      tail = {r32(chunk / 2), r32(chunk / 4), r32(chunk / 4)};
-      size_t used = 0;
-      for (size_t v : head) used += v;
-      for (size_t v : tail) used += v;
-      for (size_t v : head) sizes.push_back(v);
-      for (size_t done = used; done < n;) {
-        size_t m = std::min(chunk, n - done);
-        sizes.push_back(m);
-        done += m;
-      }
-      for (size_t v : tail) sizes.push_back(v);
-    } else {
+    {
       bool ramped = !src_dev && depth >= 2 && chunk >= 8 * 1024;
       size_t step = ramped ? chunk / P2V_RAMP_START_DIV / 32 * 32 : chunk;
       for (size_t done = 0; done < n;) {
