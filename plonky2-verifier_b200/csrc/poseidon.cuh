@@ -378,7 +378,7 @@ __device__ __forceinline__ void poseidon_mds_crt(u64 (&s)[12], int next_round) {
 //     match; both stay non-negative);
 //   * fold: raw words (Ll, K + Lh), (Hl, K + Hh), K = 0x43300000:  value = Ll + 2^32 (Lh + Hl) + 2^64 Hh =
 //     raw - K (2^32 + 2^64); c = -K (2^32 + 2^64) mod p sits in the seeds, so the fold works on the raw words:
-//     w1 = RL + Hl, w2 = RH + carry (< 2^31), result = (w1 + w2 : Ll) - w2 with one wrap fix-up: 8 ALU instructions.
+//     Z = RL + Hl + RH (< 2^33), result = (Zlo + c : Ll) - (RH + c) with c = Z >> 32: 5 ALU instructions.
 // Bounds: word sums <= 272 (2^32 - 1) + 2^34 < 2^41: exact in doubles, high field of T below 2^20.
 #ifndef POSEIDON_CVT_I2F
 #define POSEIDON_CVT_I2F 1
@@ -459,20 +459,19 @@ __device__ __forceinline__ void poseidon_crt64_pair(u64 xj, u64 xk, double (&SL)
 #endif
   poseidon_crt64_col<J, 0>(SL, DL, SH, DH, xpL, xmL, xpH, xmH);
 }
+// value = Ll + 2^32 (RL + Hl) + 2^64 RH  =  Ll - RH + 2^32 Z  with  Z = RL + Hl + RH < 2^33  (RL, RH = K + small, K < 2^31):
+// Z = Zlo + 2^32 c2 and 2^64 c2 = (2^32 - 1) c2 (mod p) give  value = (Zlo + c2 : Ll) - (RH + c2),  exact in 64 bits (no wrap of
+// Zlo + c2: c2 = 1 leaves Zlo < 2K + 2^21; no borrow out: the high word is >= 1 whenever something is subtracted).  Written on
+// 64-bit integers so that ptxas uses the three-input IADD3 with both carry outputs: 5 SASS instructions (the carry-chain form
+// in PTX, which has no three-input add.cc, took 7).
 __device__ __forceinline__ u64 poseidon_crt64_fold(double TL, double TH) {
   u32 Ll = (u32)__double2loint(TL), RL = (u32)__double2hiint(TL), Hl = (u32)__double2loint(TH), RH = (u32)__double2hiint(TH);
 #if P2V_WHATIF == 3
-  return ((u64)(RL + Hl + RH) << 32) | Ll;  // no modular fold (2 adds instead of 8 instructions)
+  return ((u64)(RL + Hl + RH) << 32) | Ll;  // no modular fold
 #endif
-  u32 r0, r1;
-  asm("{\n\t.reg .u32 w2,c;\n\t"
-      "add.cc.u32 %1,%3,%4;\n\taddc.u32 w2,%5,0;\n\t"
-      "add.cc.u32 %1,%1,w2;\n\taddc.u32 c,0,0;\n\t"
-      "add.u32 w2,w2,c;\n\tadd.u32 %1,%1,c;\n\t"
-      "sub.cc.u32 %0,%2,w2;\n\tsubc.u32 %1,%1,0;\n\t}"
-      : "=&r"(r0), "=&r"(r1)
-      : "r"(Ll), "r"(RL), "r"(Hl), "r"(RH));
-  return ((u64)r1 << 32) | r0;
+  u64 Z = (u64)RL + (u64)Hl + (u64)RH;
+  u32 c2 = (u32)(Z >> 32), Zlo = (u32)Z;
+  return ((((u64)(Zlo + c2)) << 32) | Ll) - (u64)(RH + c2);
 }
 __device__ __forceinline__ void poseidon_crt64_seed(double (&SL)[6], double (&DL)[6], double (&SH)[6], double (&DH)[6], int next_round) {
 #pragma unroll
@@ -514,6 +513,151 @@ __device__ __forceinline__ void poseidon_mds_crt64(u64 (&s)[12], int next_round)
   poseidon_crt64_pair<0>(s[0], s[6], SL, DL, SH, DH);
   poseidon_crt64_finish(s, s[0], SL, DL, SH, DH);
 }
+// ---- second CRT level on the cyclic half (POSEIDON_CRT_LEVEL2) -------------------------------------------------------
+// S'_i = sum_j p'_{(j-i) mod 6} X_j is a 6-point CYCLIC convolution, and x^6 - 1 = (x^3 - 1)(x^3 + 1): with
+// A_k = X_k + X_{k+3}, B_k = X_k - X_{k+3},  p'_e + p'_{e+3} = (32,32,64),  p'_e - p'_{e+3} = (-2,-4,16), halved again:
+//     SS_i = 16 (A_0 + A_1 + A_2) + 16 A_{(i+2) mod 3}            SD_i = sum_k m_{(k-i) mod 6} B_k,  m = (-1,-2,8,1,2,-8)
+//     S'_i = SS_i + SD_i,   S'_{i+3} = SS_i - SD_i                 (i < 3)
+// The cyclic part collapses to additions and one scale by 16 that rides on the recombining DFMA: 29 FP64 operations
+// instead of 36 per part.  Seeds: SD_i starts from g_i, E_i = A_0 + A_1 + A_2 + A_{(i+2)%3} gets e_i (a multiple of 1/16 next to
+// 2^48: exact), with 16 e_i + g_i = 2^52 + sigma_i and 16 e_i - g_i = 2^52 + sigma_{i+3}; that needs sigma_i + sigma_{i+3} even, which
+// the table builder arranges with value-preserving moves (multiples of 2p, 2^33 between the parts) on a_{i+3}.
+#ifndef POSEIDON_CRT_LEVEL2
+#define POSEIDON_CRT_LEVEL2 1
+#endif
+#if POSEIDON_CRT_LEVEL2
+// one 16-byte aligned row of 24 seeds per round, in the order they are consumed (ptxas fetches them with 128-bit uniform loads):
+// [0..5] D' low, [6..11] D' high, [12..14] e low, [15..17] g low, [18..20] e high, [21..23] g high
+struct alignas(16) PoseidonRcCrt64L2 {
+  double v[31][24];
+};
+enum { L2_DL = 0, L2_DH = 6, L2_EL = 12, L2_GL = 15, L2_EH = 18, L2_GH = 21 };
+constexpr PoseidonRcCrt64L2 poseidon_make_rc_crt64_l2() {
+  constexpr u64 rc[360] = P2V_ALL_ROUND_CONSTANTS;
+  constexpr u64 kadj = ((u64)P2V_F64_K << 33) - (u64)P2V_F64_K;
+  constexpr u64 cadj = GL_P - kadj;
+  PoseidonRcCrt64L2 t{};
+  for (int r = 0; r < 31; r++) {
+    u64 alo[6] = {}, ahi[6] = {}, blo[6] = {}, bhi[6] = {};
+    for (int i = 0; i < 6; i++) {
+      u64 ra = r < 30 ? rc[r * 12 + i] : 0, rb = r < 30 ? rc[r * 12 + i + 6] : 0;
+      if (ra >= GL_P) ra -= GL_P;
+      if (rb >= GL_P) rb -= GL_P;
+      u64 a = poseidon_addmod_c(ra, cadj), b = poseidon_addmod_c(rb, cadj);
+      alo[i] = a & 0xFFFFFFFFULL; ahi[i] = a >> 32; blo[i] = b & 0xFFFFFFFFULL; bhi[i] = b >> 32;
+      bool flo = ((alo[i] ^ blo[i]) & 1) != 0, fhi = ((ahi[i] ^ bhi[i]) & 1) != 0;
+      if (flo && fhi) { blo[i] += 1; bhi[i] += 0xFFFFFFFFULL; }
+      else if (flo) { blo[i] += 1 + (1ULL << 32); bhi[i] += 0xFFFFFFFEULL; }
+      else if (fhi) {
+        if (bhi[i] >= 1) { blo[i] += 1ULL << 32; bhi[i] -= 1; }
+        else { blo[i] += 2 + (1ULL << 32); bhi[i] += 2 * 0xFFFFFFFFULL - 1; }
+      }
+    }
+    for (int i = 0; i < 3; i++) {
+      // sigma = (a + b) / 2 per part; make sigma_i + sigma_{i+3} even in both parts by moving a_{i+3} (all increments even)
+      bool olo = (((alo[i] + blo[i]) / 2 + (alo[i + 3] + blo[i + 3]) / 2) & 1) != 0;
+      bool ohi = (((ahi[i] + bhi[i]) / 2 + (ahi[i + 3] + bhi[i + 3]) / 2) & 1) != 0;
+      if (olo && ohi) { alo[i + 3] += 2; ahi[i + 3] += (1ULL << 33) - 2; }                        // + 2p
+      else if (olo) { alo[i + 3] += 2 + (1ULL << 33); ahi[i + 3] += (1ULL << 33) - 4; }          // + 2p, 2^33 moved down
+      else if (ohi) { alo[i + 3] += 4 + (1ULL << 33); ahi[i + 3] += (1ULL << 34) - 6; }          // both of the above
+    }
+    for (int i = 0; i < 6; i++) {
+      t.v[r][L2_DL + i] = (double)(((long long)alo[i] - (long long)blo[i]) / 2);
+      t.v[r][L2_DH + i] = (double)(((long long)ahi[i] - (long long)bhi[i]) / 2);
+    }
+    for (int i = 0; i < 3; i++) {
+      long long sl0 = (long long)((alo[i] + blo[i]) / 2), sl3 = (long long)((alo[i + 3] + blo[i + 3]) / 2);
+      long long sh0 = (long long)((ahi[i] + bhi[i]) / 2), sh3 = (long long)((ahi[i + 3] + bhi[i + 3]) / 2);
+      t.v[r][L2_EL + i] = P2V_TWO52 / 16.0 + (double)((sl0 + sl3) / 2) / 16.0;
+      t.v[r][L2_GL + i] = (double)((sl0 - sl3) / 2);
+      t.v[r][L2_EH + i] = P2V_TWO52 / 16.0 + (double)((sh0 + sh3) / 2) / 16.0;
+      t.v[r][L2_GH + i] = (double)((sh0 - sh3) / 2);
+    }
+  }
+  return t;
+}
+static __constant__ PoseidonRcCrt64L2 c_rc64l2 = poseidon_make_rc_crt64_l2();
+
+// pair J: conversions, butterfly, the D' half accumulated at once (column-major), X+ kept for the second level
+template <int J, int I>
+__device__ __forceinline__ void poseidon_l2_dcol(double (&DL)[6], double (&DH)[6], double xmL, double xmH) {
+  constexpr int Qc[6] = POSEIDON_MDS_QH;
+  constexpr int d = (J - I + 12) % 12;
+  constexpr double qc = (double)(d < 6 ? Qc[d] : -Qc[d - 6]);
+  DL[I] = fma(xmL, qc, DL[I]);
+  DH[I] = fma(xmH, qc, DH[I]);
+  if constexpr (I + 1 < 6) poseidon_l2_dcol<J, I + 1>(DL, DH, xmL, xmH);
+}
+template <int J>
+__device__ __forceinline__ void poseidon_l2_pair(u64 xj, u64 xk, double (&XL)[6], double (&XH)[6], double (&DL)[6], double (&DH)[6]) {
+  double bjl = __uint2double_rn((u32)xj), bjh = __uint2double_rn((u32)(xj >> 32));
+  double bkl = __uint2double_rn((u32)xk), bkh = __uint2double_rn((u32)(xk >> 32));
+  XL[J] = bjl + bkl;
+  XH[J] = bjh + bkh;
+  poseidon_l2_dcol<J, 0>(DL, DH, bjl - bkl, bjh - bkh);
+}
+// S' of one part from the six X+ (second CRT level)
+__device__ __forceinline__ void poseidon_l2_s(const double (&X)[6], const double (&e)[3], const double (&g)[3], double (&S)[6]) {
+  double A0 = X[0] + X[3], A1 = X[1] + X[4], A2 = X[2] + X[5];
+  double B0 = X[0] - X[3], B1 = X[1] - X[4], B2 = X[2] - X[5];
+  double sum = (A0 + A1) + A2;
+  double E0 = (A2 + e[0]) + sum, E1 = (A0 + e[1]) + sum, E2 = (A1 + e[2]) + sum;
+  // SD_i = sum_k m_{(k-i) mod 6} B_k, m = (-1,-2,8,1,2,-8)
+  double SD0 = fma(B2, 8.0, fma(B1, -2.0, g[0] - B0));
+  double SD1 = fma(B0, -8.0, fma(B2, -2.0, g[1] - B1));
+  double SD2 = fma(B1, -8.0, fma(B0, 2.0, g[2] - B2));
+  S[0] = fma(E0, 16.0, SD0); S[3] = fma(E0, 16.0, -SD0);
+  S[1] = fma(E1, 16.0, SD1); S[4] = fma(E1, 16.0, -SD1);
+  S[2] = fma(E2, 16.0, SD2); S[5] = fma(E2, 16.0, -SD2);
+}
+__device__ __forceinline__ void poseidon_l2_seed_d(double (&DL)[6], double (&DH)[6], int next_round) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    DL[i] = c_rc64l2.v[next_round][L2_DL + i];
+    DH[i] = c_rc64l2.v[next_round][L2_DH + i];
+  }
+}
+__device__ __forceinline__ void poseidon_l2_finish(u64 (&s)[12], u64 x0, const double (&XL)[6], const double (&XH)[6], const double (&DL)[6],
+                                                   const double (&DH)[6], int next_round) {
+  double el[3], gl[3], eh[3], gh[3], SL[6], SH[6];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    el[i] = c_rc64l2.v[next_round][L2_EL + i];
+    gl[i] = c_rc64l2.v[next_round][L2_GL + i];
+    eh[i] = c_rc64l2.v[next_round][L2_EH + i];
+    gh[i] = c_rc64l2.v[next_round][L2_GH + i];
+  }
+  poseidon_l2_s(XL, el, gl, SL);
+  poseidon_l2_s(XH, eh, gh, SH);
+  poseidon_crt64_finish(s, x0, SL, DL, SH, DH);
+}
+__device__ __forceinline__ void poseidon_mds_crt64_l2(u64 (&s)[12], int next_round) {
+  double XL[6], XH[6], DL[6], DH[6];
+  poseidon_l2_seed_d(DL, DH, next_round);
+  poseidon_l2_pair<1>(s[1], s[7], XL, XH, DL, DH);
+  poseidon_l2_pair<2>(s[2], s[8], XL, XH, DL, DH);
+  poseidon_l2_pair<3>(s[3], s[9], XL, XH, DL, DH);
+  poseidon_l2_pair<4>(s[4], s[10], XL, XH, DL, DH);
+  poseidon_l2_pair<5>(s[5], s[11], XL, XH, DL, DH);
+  poseidon_l2_pair<0>(s[0], s[6], XL, XH, DL, DH);
+  poseidon_l2_finish(s, s[0], XL, XH, DL, DH, next_round);
+}
+__device__ __forceinline__ void poseidon_full_round_crt64_l2(u64 (&s)[12], int next_round) {
+  double XL[6], XH[6], DL[6], DH[6];
+  poseidon_l2_seed_d(DL, DH, next_round);
+  u64 x0 = 0;
+#define P2V_FR_PAIR(J)                                             \
+  {                                                                \
+    u64 a = poseidon_sbox(s[J]), b = poseidon_sbox(s[J + 6]);      \
+    if (J == 0) x0 = a;                                            \
+    poseidon_l2_pair<J>(a, b, XL, XH, DL, DH);                     \
+  }
+  P2V_FR_PAIR(1) P2V_FR_PAIR(2) P2V_FR_PAIR(3) P2V_FR_PAIR(4) P2V_FR_PAIR(5) P2V_FR_PAIR(0)
+#undef P2V_FR_PAIR
+  poseidon_l2_finish(s, x0, XL, XH, DL, DH, next_round);
+}
+#endif
+
 // full round with the s-boxes and the layer in ONE basic block: the FP64/ALU work of a pair is independent of the
 // s-boxes still to come, so ptxas can interleave it with their wide multiplies (POSEIDON_SPLIT_ROUNDS)
 __device__ __forceinline__ void poseidon_full_round_crt64(u64 (&s)[12], int next_round) {
@@ -543,7 +687,9 @@ __device__ __forceinline__ void poseidon_full_round_crt64(u64 (&s)[12], int next
 #define POSEIDON_SPLIT_ROUNDS 1
 #endif
 __device__ __forceinline__ void poseidon_mds_layer(u64 (&s)[12], int next_round) {
-#if POSEIDON_MDS_F64 == 4
+#if POSEIDON_MDS_F64 == 4 && POSEIDON_CRT_LEVEL2
+  poseidon_mds_crt64_l2(s, next_round);
+#elif POSEIDON_MDS_F64 == 4
   poseidon_mds_crt64(s, next_round);
 #elif POSEIDON_MDS_F64 == 3
   poseidon_mds_crt(s, next_round);
@@ -567,7 +713,9 @@ __device__ __forceinline__ void poseidon_permute(u64 (&s)[12]) {
       int r0 = ph ? 26 : 0;
 #pragma unroll 1
       for (int r = r0; r < r0 + 4; r++) {
-#if POSEIDON_MDS_F64 == 4
+#if POSEIDON_MDS_F64 == 4 && POSEIDON_CRT_LEVEL2
+        poseidon_full_round_crt64_l2(s, r + 1);
+#elif POSEIDON_MDS_F64 == 4
         poseidon_full_round_crt64(s, r + 1);
 #else
 #pragma unroll
