@@ -24,6 +24,7 @@ struct p2v_ctx {
   // per lane: K4/K5 (transcript, constraints) run on a side stream next to the leaf phase of the Merkle kernel
   cudaStream_t side_stream[P2V_MAX_DEPTH] = {};
   cudaEvent_t staged_ev[P2V_MAX_DEPTH] = {}, transcript_ev[P2V_MAX_DEPTH] = {};
+  int prio_hi = 0, prio_lo = 0;    // cudaDeviceGetStreamPriorityRange: greatest (numerically lowest) and least priority
   int pipeline = 4;                // 1 = strictly serial chunks (per-section timings valid), 2..P2V_MAX_DEPTH = overlapped
   cudaEvent_t fork_ev = nullptr;
   std::string err;
@@ -37,6 +38,10 @@ struct p2v_ctx {
   size_t stage_bytes = 0;
   int stage_count = 0;
   cudaEvent_t stage_filled[P2V_MAX_DEPTH + 1] = {}, stage_free[P2V_MAX_DEPTH + 1] = {};
+  // host input, transcript-first schedule: the per-proof parts of a whole window of chunks are copied ahead of the query parts
+  void *pp_stage = nullptr;  // [window][proof_words]
+  size_t pp_stage_bytes = 0;
+  cudaEvent_t pp_filled = nullptr, k0_done[P2V_MAX_DEPTH] = {}, lane_done[P2V_MAX_DEPTH] = {};
   cudaEvent_t ev[8] = {};
   // Private stream-ordered pool for the staged copies of host inputs/outputs (DevIn/DevOut).  Its release
   // threshold is unlimited: with the default pool (threshold 0) every synchronisation hands the freed blocks
@@ -72,6 +77,30 @@ static inline int p2v_fail(p2v_ctx *ctx, int code, const std::string &msg) {
     P2V_CUDA((ctx), cudaGetLastError());                                        \
   } while (0)
 #define P2V_LAUNCH(ctx, kernel, grid, block, smem, ...) P2V_LAUNCH_ON(ctx, (ctx)->stream, kernel, grid, block, smem, __VA_ARGS__)
+
+// Launch with an execution priority (cudaLaunchAttributePriority; numerically LOWER = scheduled first when SM resources
+// free up — running blocks are never pre-empted).  The chunk pipeline uses it to let the short latency-bound kernels of a
+// chunk (K0, K4, K5) and the closing kernels of the OLDEST chunk overtake the bulk Merkle blocks of younger chunks.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t p2v_launch_prio(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t strm, int prio, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = strm;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributePriority;
+  at[0].val.priority = prio;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define P2V_LAUNCH_PRIO(ctx, strm, prio, kernel, grid, block, smem, ...)                                   \
+  do {                                                                                                     \
+    P2V_CUDA((ctx), p2v_launch_prio(kernel, dim3(grid), dim3(block), (smem), (strm), (prio), __VA_ARGS__)); \
+    (ctx)->launches++;                                                                                     \
+    P2V_CUDA((ctx), cudaGetLastError());                                                                   \
+  } while (0)
 
 static inline bool p2v_is_device_ptr(const void *p) {
   cudaPointerAttributes a;

@@ -6,6 +6,7 @@ thread_local std::string p2v_tls_error;
 
 // streams, events and the private pool of a new context; on failure the caller destroys the partly built context
 static int ctxInit(p2v_ctx *ctx, int device) {
+  P2V_CUDA(nullptr, cudaDeviceGetStreamPriorityRange(&ctx->prio_lo, &ctx->prio_hi));
   P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (int i = 1; i < P2V_MAX_DEPTH; i++) {
@@ -16,8 +17,11 @@ static int ctxInit(p2v_ctx *ctx, int device) {
     P2V_CUDA(nullptr, cudaStreamCreateWithFlags(&ctx->side_stream[i], cudaStreamNonBlocking));
     P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->staged_ev[i], cudaEventDisableTiming));
     P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->transcript_ev[i], cudaEventDisableTiming));
+    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->k0_done[i], cudaEventDisableTiming));
+    P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->lane_done[i], cudaEventDisableTiming));
   }
   P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+  P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->pp_filled, cudaEventDisableTiming));
   for (auto &ev : ctx->ev) P2V_CUDA(nullptr, cudaEventCreate(&ev));
   for (int i = 0; i < P2V_MAX_DEPTH + 1; i++) {
     P2V_CUDA(nullptr, cudaEventCreateWithFlags(&ctx->stage_filled[i], cudaEventDisableTiming));
@@ -79,7 +83,11 @@ void p2v_ctx_destroy(p2v_ctx *ctx) {
     if (ctx->side_stream[i]) { cudaStreamSynchronize(ctx->side_stream[i]); cudaStreamDestroy(ctx->side_stream[i]); }
     if (ctx->staged_ev[i]) cudaEventDestroy(ctx->staged_ev[i]);
     if (ctx->transcript_ev[i]) cudaEventDestroy(ctx->transcript_ev[i]);
+    if (ctx->k0_done[i]) cudaEventDestroy(ctx->k0_done[i]);
+    if (ctx->lane_done[i]) cudaEventDestroy(ctx->lane_done[i]);
   }
+  if (ctx->pp_filled) cudaEventDestroy(ctx->pp_filled);
+  if (ctx->pp_stage) cudaFree(ctx->pp_stage);
   p2v_nccl_finalize(ctx);
   if (ctx->ws) cudaFree(ctx->ws);
   for (int i = 1; i < P2V_MAX_DEPTH; i++) {

@@ -482,24 +482,28 @@ __device__ __forceinline__ void poseidon_crt64_seed(double (&SL)[6], double (&DL
     DH[i] = c_rc64.dh[next_round][i];
   }
 }
-// x0 = the value of lane 0 that entered the layer (for the +8 on the diagonal)
-__device__ __forceinline__ void poseidon_crt64_finish(u64 (&s)[12], u64 x0, const double (&SL)[6], const double (&DL)[6],
-                                                      const double (&SH)[6], const double (&DH)[6]) {
+// (l0, h0) = the two parts of the value of lane 0 that entered the layer (for the +8 on the diagonal)
+__device__ __forceinline__ void poseidon_crt64_finish_d(u64 (&s)[12], double l0, double h0, const double (&SL)[6], const double (&DL)[6],
+                                                        const double (&SH)[6], const double (&DH)[6]) {
 #pragma unroll
   for (int i = 0; i < 6; i++) {
     double TL = SL[i] + DL[i], UL = SL[i] - DL[i], TH = SH[i] + DH[i], UH = SH[i] - DH[i];
     if (i == 0) {
-#if POSEIDON_CVT_I2F
-      double l0 = __uint2double_rn((u32)x0), h0 = __uint2double_rn((u32)(x0 >> 32));
-#else
-      double l0 = __hiloint2double((int)P2V_F64_K, (int)(u32)x0) - P2V_TWO52, h0 = __hiloint2double((int)P2V_F64_K, (int)(u32)(x0 >> 32)) - P2V_TWO52;
-#endif
       TL = fma(l0, 8.0, TL);
       TH = fma(h0, 8.0, TH);
     }
     s[i] = poseidon_crt64_fold(TL, TH);
     s[i + 6] = poseidon_crt64_fold(UL, UH);
   }
+}
+__device__ __forceinline__ void poseidon_crt64_finish(u64 (&s)[12], u64 x0, const double (&SL)[6], const double (&DL)[6],
+                                                      const double (&SH)[6], const double (&DH)[6]) {
+#if POSEIDON_CVT_I2F
+  double l0 = __uint2double_rn((u32)x0), h0 = __uint2double_rn((u32)(x0 >> 32));
+#else
+  double l0 = __hiloint2double((int)P2V_F64_K, (int)(u32)x0) - P2V_TWO52, h0 = __hiloint2double((int)P2V_F64_K, (int)(u32)(x0 >> 32)) - P2V_TWO52;
+#endif
+  poseidon_crt64_finish_d(s, l0, h0, SL, DL, SH, DH);
 }
 // the whole layer; pair 0 (the one lane 0 of a partial round feeds) is accumulated last
 __device__ __forceinline__ void poseidon_mds_crt64(u64 (&s)[12], int next_round) {
@@ -525,6 +529,9 @@ __device__ __forceinline__ void poseidon_mds_crt64(u64 (&s)[12], int next_round)
 #ifndef POSEIDON_CRT_LEVEL2
 #define POSEIDON_CRT_LEVEL2 1
 #endif
+#ifndef POSEIDON_FUSE_SBOX
+#define POSEIDON_FUSE_SBOX 1 /* 1: full rounds hand the last product of x^7 to the layer unreduced; 2: partial rounds too */
+#endif
 #if POSEIDON_CRT_LEVEL2
 // one 16-byte aligned row of 24 seeds per round, in the order they are consumed (ptxas fetches them with 128-bit uniform loads):
 // [0..5] D' low, [6..11] D' high, [12..14] e low, [15..17] g low, [18..20] e high, [21..23] g high
@@ -545,6 +552,13 @@ constexpr PoseidonRcCrt64L2 poseidon_make_rc_crt64_l2() {
       if (rb >= GL_P) rb -= GL_P;
       u64 a = poseidon_addmod_c(ra, cadj), b = poseidon_addmod_c(rb, cadj);
       alo[i] = a & 0xFFFFFFFFULL; ahi[i] = a >> 32; blo[i] = b & 0xFFFFFFFFULL; bhi[i] = b >> 32;
+#if POSEIDON_FUSE_SBOX
+      // raw s-box products enter the layer with a low part in (-2^34, 2^32): lift the low parts by 2^42 and take 2^10 off the
+      // high parts (same value); a high part below 2^10 is first moved up by p = 1 + 2^32 (2^32 - 1)
+      if (ahi[i] < 1024) { alo[i] += 1; ahi[i] += 0xFFFFFFFFULL; }
+      if (bhi[i] < 1024) { blo[i] += 1; bhi[i] += 0xFFFFFFFFULL; }
+      alo[i] += 1ULL << 42; blo[i] += 1ULL << 42; ahi[i] -= 1024; bhi[i] -= 1024;
+#endif
       bool flo = ((alo[i] ^ blo[i]) & 1) != 0, fhi = ((ahi[i] ^ bhi[i]) & 1) != 0;
       if (flo && fhi) { blo[i] += 1; bhi[i] += 0xFFFFFFFFULL; }
       else if (flo) { blo[i] += 1 + (1ULL << 32); bhi[i] += 0xFFFFFFFEULL; }
@@ -589,13 +603,33 @@ __device__ __forceinline__ void poseidon_l2_dcol(double (&DL)[6], double (&DH)[6
   if constexpr (I + 1 < 6) poseidon_l2_dcol<J, I + 1>(DL, DH, xmL, xmH);
 }
 template <int J>
-__device__ __forceinline__ void poseidon_l2_pair(u64 xj, u64 xk, double (&XL)[6], double (&XH)[6], double (&DL)[6], double (&DH)[6]) {
-  double bjl = __uint2double_rn((u32)xj), bjh = __uint2double_rn((u32)(xj >> 32));
-  double bkl = __uint2double_rn((u32)xk), bkh = __uint2double_rn((u32)(xk >> 32));
+__device__ __forceinline__ void poseidon_l2_pair_d(double bjl, double bjh, double bkl, double bkh, double (&XL)[6], double (&XH)[6], double (&DL)[6],
+                                                   double (&DH)[6]) {
   XL[J] = bjl + bkl;
   XH[J] = bjh + bkh;
   poseidon_l2_dcol<J, 0>(DL, DH, bjl - bkl, bjh - bkh);
 }
+template <int J>
+__device__ __forceinline__ void poseidon_l2_pair(u64 xj, u64 xk, double (&XL)[6], double (&XH)[6], double (&DL)[6], double (&DH)[6]) {
+  poseidon_l2_pair_d<J>(__uint2double_rn((u32)xj), __uint2double_rn((u32)(xj >> 32)), __uint2double_rn((u32)xk), __uint2double_rn((u32)(xk >> 32)), XL,
+                        XH, DL, DH);
+}
+#if POSEIDON_FUSE_SBOX
+// x^7 whose LAST product is handed to the layer unreduced (POSEIDON_FUSE_SBOX): x3 * x4 = w0 + 2^32 w1 + 2^64 w2 + 2^96 w3 with
+// 2^64 = 2^32 - 1 and 2^96 = -1 (mod p) is  (w0 - w2 - w3) + 2^32 (w1 + w2): the two parts the layer works on anyway, as exact
+// doubles in (-2^34, 2^32) and [0, 2^33).  4 conversions + 3 additions on the XU / FP64 pipes instead of the 10-instruction
+// carry chain + 2 conversions; the layer's seeds carry the offset that keeps its low sums non-negative.
+__device__ __forceinline__ void poseidon_sbox_raw(u64 x, double &L, double &H) {
+  u64 x2 = gl_mul(x, x);
+  u64 x3 = gl_mul(x, x2);
+  u64 x4 = gl_mul(x2, x2);
+  unsigned __int128 m = (unsigned __int128)x3 * x4;
+  u64 lo = (u64)m, hi = (u64)(m >> 64);
+  double w0 = __uint2double_rn((u32)lo), w1 = __uint2double_rn((u32)(lo >> 32)), w2 = __uint2double_rn((u32)hi), w3 = __uint2double_rn((u32)(hi >> 32));
+  L = w0 - (w2 + w3);
+  H = w1 + w2;
+}
+#endif
 // S' of one part from the six X+ (second CRT level)
 __device__ __forceinline__ void poseidon_l2_s(const double (&X)[6], const double (&e)[3], const double (&g)[3], double (&S)[6]) {
   double A0 = X[0] + X[3], A1 = X[1] + X[4], A2 = X[2] + X[5];
@@ -617,9 +651,8 @@ __device__ __forceinline__ void poseidon_l2_seed_d(double (&DL)[6], double (&DH)
     DH[i] = c_rc64l2.v[next_round][L2_DH + i];
   }
 }
-__device__ __forceinline__ void poseidon_l2_finish(u64 (&s)[12], u64 x0, const double (&XL)[6], const double (&XH)[6], const double (&DL)[6],
-                                                   const double (&DH)[6], int next_round) {
-  double el[3], gl[3], eh[3], gh[3], SL[6], SH[6];
+__device__ __forceinline__ void poseidon_l2_sums(const double (&XL)[6], const double (&XH)[6], int next_round, double (&SL)[6], double (&SH)[6]) {
+  double el[3], gl[3], eh[3], gh[3];
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     el[i] = c_rc64l2.v[next_round][L2_EL + i];
@@ -629,7 +662,19 @@ __device__ __forceinline__ void poseidon_l2_finish(u64 (&s)[12], u64 x0, const d
   }
   poseidon_l2_s(XL, el, gl, SL);
   poseidon_l2_s(XH, eh, gh, SH);
+}
+__device__ __forceinline__ void poseidon_l2_finish(u64 (&s)[12], u64 x0, const double (&XL)[6], const double (&XH)[6], const double (&DL)[6],
+                                                   const double (&DH)[6], int next_round) {
+  double SL[6], SH[6];
+  poseidon_l2_sums(XL, XH, next_round, SL, SH);
   poseidon_crt64_finish(s, x0, SL, DL, SH, DH);
+}
+// lane 0 given as its two parts (fused s-box)
+__device__ __forceinline__ void poseidon_l2_finish_d(u64 (&s)[12], double l0, double h0, const double (&XL)[6], const double (&XH)[6],
+                                                     const double (&DL)[6], const double (&DH)[6], int next_round) {
+  double SL[6], SH[6];
+  poseidon_l2_sums(XL, XH, next_round, SL, SH);
+  poseidon_crt64_finish_d(s, l0, h0, SL, DL, SH, DH);
 }
 __device__ __forceinline__ void poseidon_mds_crt64_l2(u64 (&s)[12], int next_round) {
   double XL[6], XH[6], DL[6], DH[6];
@@ -642,9 +687,39 @@ __device__ __forceinline__ void poseidon_mds_crt64_l2(u64 (&s)[12], int next_rou
   poseidon_l2_pair<0>(s[0], s[6], XL, XH, DL, DH);
   poseidon_l2_finish(s, s[0], XL, XH, DL, DH, next_round);
 }
+#if POSEIDON_FUSE_SBOX >= 2
+// partial round with the s-box of lane 0 fused into the layer
+__device__ __forceinline__ void poseidon_partial_round_crt64_l2(u64 (&s)[12], int next_round) {
+  double XL[6], XH[6], DL[6], DH[6];
+  poseidon_l2_seed_d(DL, DH, next_round);
+  poseidon_l2_pair<1>(s[1], s[7], XL, XH, DL, DH);
+  poseidon_l2_pair<2>(s[2], s[8], XL, XH, DL, DH);
+  poseidon_l2_pair<3>(s[3], s[9], XL, XH, DL, DH);
+  poseidon_l2_pair<4>(s[4], s[10], XL, XH, DL, DH);
+  poseidon_l2_pair<5>(s[5], s[11], XL, XH, DL, DH);
+  double l0, h0;
+  poseidon_sbox_raw(s[0], l0, h0);
+  poseidon_l2_pair_d<0>(l0, h0, __uint2double_rn((u32)s[6]), __uint2double_rn((u32)(s[6] >> 32)), XL, XH, DL, DH);
+  poseidon_l2_finish_d(s, l0, h0, XL, XH, DL, DH, next_round);
+}
+#endif
 __device__ __forceinline__ void poseidon_full_round_crt64_l2(u64 (&s)[12], int next_round) {
   double XL[6], XH[6], DL[6], DH[6];
   poseidon_l2_seed_d(DL, DH, next_round);
+#if POSEIDON_FUSE_SBOX
+  double x0l = 0, x0h = 0;
+#define P2V_FR_PAIR(J)                                             \
+  {                                                                \
+    double al, ah, bl, bh;                                         \
+    poseidon_sbox_raw(s[J], al, ah);                               \
+    poseidon_sbox_raw(s[J + 6], bl, bh);                           \
+    if (J == 0) { x0l = al; x0h = ah; }                            \
+    poseidon_l2_pair_d<J>(al, ah, bl, bh, XL, XH, DL, DH);         \
+  }
+  P2V_FR_PAIR(1) P2V_FR_PAIR(2) P2V_FR_PAIR(3) P2V_FR_PAIR(4) P2V_FR_PAIR(5) P2V_FR_PAIR(0)
+#undef P2V_FR_PAIR
+  poseidon_l2_finish_d(s, x0l, x0h, XL, XH, DL, DH, next_round);
+#else
   u64 x0 = 0;
 #define P2V_FR_PAIR(J)                                             \
   {                                                                \
@@ -655,6 +730,7 @@ __device__ __forceinline__ void poseidon_full_round_crt64_l2(u64 (&s)[12], int n
   P2V_FR_PAIR(1) P2V_FR_PAIR(2) P2V_FR_PAIR(3) P2V_FR_PAIR(4) P2V_FR_PAIR(5) P2V_FR_PAIR(0)
 #undef P2V_FR_PAIR
   poseidon_l2_finish(s, x0, XL, XH, DL, DH, next_round);
+#endif
 }
 #endif
 
@@ -726,8 +802,12 @@ __device__ __forceinline__ void poseidon_permute(u64 (&s)[12]) {
     } else {
 #pragma unroll 1
       for (int r = 4; r < 26; r++) {
+#if POSEIDON_MDS_F64 == 4 && POSEIDON_CRT_LEVEL2 && POSEIDON_FUSE_SBOX >= 2
+        poseidon_partial_round_crt64_l2(s, r + 1);
+#else
         s[0] = poseidon_sbox(s[0]);
         poseidon_mds_layer(s, r + 1);
+#endif
       }
     }
   }

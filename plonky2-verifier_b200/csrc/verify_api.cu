@@ -200,6 +200,23 @@ int ensureStage(p2v_ctx *ctx, size_t bytes, int count) {
   return P2V_OK;
 }
 
+// Host input, transcript-first schedule: one buffer for the per-proof parts of a whole window of chunks
+int ensurePpStage(p2v_ctx *ctx, size_t bytes) {
+  if (ctx->pp_stage_bytes >= bytes) return P2V_OK;
+  P2V_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  for (int i = 0; i < P2V_MAX_DEPTH; i++) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->side_stream[i]));
+  if (ctx->pp_stage) cudaFree(ctx->pp_stage);
+  ctx->pp_stage = nullptr;
+  ctx->pp_stage_bytes = 0;
+  cudaError_t e = cudaMalloc(&ctx->pp_stage, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return p2v_fail(ctx, P2V_E_NOMEM, std::string("staging buffer allocation failed: ") + cudaGetErrorString(e));
+  }
+  ctx->pp_stage_bytes = bytes;
+  return P2V_OK;
+}
+
 enum { RUN_CHALLENGES = 1, RUN_CONSTRAINTS = 2, RUN_FRI = 4 };
 
 struct Outputs {
@@ -291,10 +308,11 @@ struct Job {
 struct JobState {  // everything runJobs keeps per job while the chunks are in flight
   bool src_dev = false;
   size_t chunk = 0, blob_words = 0;
+  size_t window = 0;  // host input, transcript-first schedule: proofs whose per-proof parts are copied ahead in one piece (0 = off)
   DevOut o_ch, o_comb, o_eq, o_status, o_bits, o_qs, o_folded, o_roots;
   DevIn i_ch;
 };
-struct Chunk { int job; size_t c0, m; };
+struct Chunk { int job; size_t c0, m; size_t win_n = 0; };  // win_n > 0: first chunk of a window of win_n proofs (transcript-first schedule)
 
 int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
   auto host_t0 = std::chrono::steady_clock::now();
@@ -350,6 +368,23 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
     if ((rc = ensureWorkspace(ctx, k, ws_bytes))) return rc;
   const int nstage_bufs = depth + 1;  // one per lane in flight + one being filled
   if (stage_bytes && (rc = ensureStage(ctx, stage_bytes, nstage_bufs))) return rc;
+  // Host input on the pipeline: transcript-first schedule (P2V_PPFIRST=0 switches it off).  The per-proof parts (5.5% of a
+  // blob at the standard shape) of a whole WINDOW of chunks are copied first with one strided copy, the query parts follow
+  // chunk by chunk (strided as well, so every byte still crosses PCIe once).  K0/K4/K5 of a chunk — a latency-bound chain of
+  // 114 dependent permutations per proof, ~10 ms next to the Merkle blocks of other chunks — then run long before the chunk's
+  // query parts arrive, and what is left after the LAST copy is the Merkle work of one short chunk instead of that chain.
+  static const bool pp_first_on = !(getenv("P2V_PPFIRST") && atoi(getenv("P2V_PPFIRST")) == 0);
+  const size_t win_bytes = getenv("P2V_PPFIRST_BYTES") ? (size_t)atoll(getenv("P2V_PPFIRST_BYTES")) : ((size_t)1 << 30);  // test hook: small windows
+  size_t pp_bytes = 0;
+  if (pp_first_on && depth >= 2)
+    for (size_t g = 0; g < jobs.size(); g++) {
+      if (!live(g) || js[g].src_dev) continue;
+      const size_t row = (size_t)jobs[g].cir->dev.L.proof_words * 8;
+      size_t w = std::max<size_t>(1, win_bytes / row / js[g].chunk) * js[g].chunk;  // ~1 GiB of per-proof parts, whole chunks
+      js[g].window = std::min(w, (jobs[g].n + 31) / 32 * 32);
+      pp_bytes = std::max(pp_bytes, js[g].window * row);
+    }
+  if (pp_bytes && (rc = ensurePpStage(ctx, pp_bytes))) return rc;
   // ---- outputs that may live on the host (temporaries are allocated in stream order on the primary stream) ---------------
   for (size_t g = 0; g < jobs.size(); g++) {
     if (!live(g)) continue;
@@ -395,6 +430,13 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
   const bool timed = depth == 1;
   static const int force_split = getenv("P2V_SPLIT") ? atoi(getenv("P2V_SPLIT")) : -1;
   static const bool trace_on = getenv("P2V_TRACE") != nullptr;
+  // Launch priorities (P2V_PRIO: 0 = none, 1 = K0/K4/K5 first, 2 = also the closing kernels of a chunk before younger chunks' leaf
+  // blocks) and the tail of the host-input schedule (P2V_TAIL: the last chunk is halved repeatedly down to this many proofs)
+  static const int prio_mode = getenv("P2V_PRIO") ? atoi(getenv("P2V_PRIO")) : 0;
+  static const size_t tail_min = getenv("P2V_TAIL") ? (size_t)atol(getenv("P2V_TAIL")) : 0;
+  const int prio_head = prio_mode >= 1 ? ctx->prio_hi : 0;
+  const int prio_close = prio_mode >= 2 ? std::min(ctx->prio_lo, ctx->prio_hi + 1) : 0;
+  const int prio_bulk = prio_mode >= 1 ? ctx->prio_lo : 0;
   std::vector<TracePoint> trace;
   auto mark = [&](const char *what_, int chunk_i, size_t m_i, cudaStream_t s) {
     if (!trace_on) return;
@@ -428,14 +470,35 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
         done += m;
         if (ramped) step = std::min(chunk, (step * P2V_RAMP_NUM / P2V_RAMP_DEN + 31) / 32 * 32);
       }
+      // tail: what is left when the last copy ends is the whole latency of the last chunk — make the last chunks short
+      if (!src_dev && depth >= 2 && tail_min >= 32)
+        while (sizes.back() >= 2 * tail_min) {
+          size_t last = sizes.back(), half = (last / 2 + 31) / 32 * 32;
+          sizes.back() = half;
+          sizes.push_back(last - half);
+        }
     }
-    size_t c0 = 0;
-    for (size_t m : sizes) {
-      sched.push_back({(int)g, c0, m});
+    size_t c0 = 0, win_left = 0;
+    for (size_t i = 0; i < sizes.size(); i++) {
+      const size_t m = sizes[i];
+      Chunk ck{(int)g, c0, m};
+      if (js[g].window) {
+        if (win_left == 0) {
+          // a new window starts here: as many whole chunks as fit (at least this one)
+          size_t wn = m;
+          for (size_t j = i + 1; j < sizes.size() && wn + sizes[j] <= js[g].window; j++) wn += sizes[j];
+          ck.win_n = wn;
+          win_left = wn;
+        }
+        win_left -= m;
+      }
+      sched.push_back(ck);
       c0 += m;
     }
   }
   int nstaged = 0;  // host-input chunks issued so far: they alternate between the two staging buffers
+  bool k0_recorded[P2V_MAX_DEPTH] = {}, lane_recorded[P2V_MAX_DEPTH] = {};
+  std::vector<size_t> win_base(jobs.size(), 0);
   for (int k = 0; k < (int)sched.size(); k++) {
     const Chunk &ck = sched[k];
     const Job &job = jobs[ck.job];
@@ -451,13 +514,35 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
     carve(d, m, (char *)(lane == 0 ? ctx->ws : ctx->lane_ws[lane]), &ws, out.folded != nullptr, out.roots != nullptr);
     ws.ch_in = t.i_ch.as<u64>(); ws.ch_in_n = n; ws.ch_in_off = c0;
     int b = -1;
+    const bool pp_first = !src_dev && t.window > 0;
+    const size_t pw = (size_t)d.L.proof_words;
+    if (pp_first && ck.win_n) {
+      // the per-proof parts of the whole window, ahead of its query parts; the buffer is reused, so every K0 of the previous
+      // window (the ones that can still be pending are the last one of each lane) must have read it
+      for (int i = 0; i < depth; i++)
+        if (k0_recorded[i]) P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->k0_done[i], 0));
+      mark("pp_copy_start", k, ck.win_n, ctx->copy_stream);
+      P2V_CUDA(ctx, cudaMemcpy2DAsync(ctx->pp_stage, pw * 8, src, blob_words * 8, pw * 8, ck.win_n, cudaMemcpyHostToDevice, ctx->copy_stream));
+      P2V_CUDA(ctx, cudaEventRecord(ctx->pp_filled, ctx->copy_stream));
+      mark("pp_copy_end", k, ck.win_n, ctx->copy_stream);
+      win_base[ck.job] = c0;
+    }
+    ws.aos_pitch = blob_words;
+    ws.aos_qoff = d.L.proof_words;
     if (!src_dev) {
       // staging ring: the H2D copy of the next chunks overlaps the kernels of the current ones; buffer b is free again
       // once the last kernel that reads it (the chunk that used it depth + 1 staged chunks ago) has finished
       b = nstaged++ % nstage_bufs;
       P2V_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[b], 0));
       mark("copy_start", k, m, ctx->copy_stream);
-      P2V_CUDA(ctx, cudaMemcpyAsync(ctx->stage_buf[b], src, m * blob_words * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      if (pp_first) {
+        const size_t qw = blob_words - pw;  // the query parts only, packed
+        P2V_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_buf[b], qw * 8, src + pw, blob_words * 8, qw * 8, m, cudaMemcpyHostToDevice, ctx->copy_stream));
+        ws.aos_pitch = qw;
+        ws.aos_qoff = 0;
+      } else {
+        P2V_CUDA(ctx, cudaMemcpyAsync(ctx->stage_buf[b], src, m * blob_words * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      }
       P2V_CUDA(ctx, cudaEventRecord(ctx->stage_filled[b], ctx->copy_stream));
       mark("copy_end", k, m, ctx->copy_stream);
       P2V_CUDA(ctx, cudaStreamWaitEvent(st, ctx->stage_filled[b], 0));
@@ -466,13 +551,27 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
     ws.aos = src;
     // K0
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    const bool split = (what & RUN_FRI) && (force_split >= 0 ? force_split == 1 : !src_dev);
+    cudaStream_t side = ((split || pp_first) && depth >= 2) ? ctx->side_stream[lane] : st;
     {
       // only the per-proof part is transposed; the query parts are read in place
       dim3 grid((unsigned)((m + 31) / 32), (unsigned)((d.L.proof_words + 31) / 32));
-      P2V_LAUNCH_ON(ctx, st, k_stage_transpose, grid, 256, 0, src, m, (int)blob_words, d.L.proof_words, d.L.query_words, d.Q, ws.pp, (u64 *)nullptr,
-                    d.L.proof_words);
+      if (pp_first) {
+        // K0 on the side stream, from the window's buffer: it waits for the window's copy and for the previous chunk of this
+        // lane (whose kernels still read the lane's planes), not for this chunk's query parts
+        if (lane_recorded[lane]) P2V_CUDA(ctx, cudaStreamWaitEvent(side, ctx->lane_done[lane], 0));
+        P2V_CUDA(ctx, cudaStreamWaitEvent(side, ctx->pp_filled, 0));
+        const u64 *ppsrc = (const u64 *)ctx->pp_stage + (c0 - win_base[ck.job]) * pw;
+        P2V_LAUNCH_PRIO(ctx, side, prio_head, k_stage_transpose, grid, 256, 0, ppsrc, m, d.L.proof_words, d.L.proof_words, d.L.query_words, d.Q, ws.pp,
+                        (u64 *)nullptr, d.L.proof_words);
+        P2V_CUDA(ctx, cudaEventRecord(ctx->k0_done[lane], side));
+        k0_recorded[lane] = true;
+      } else {
+        P2V_LAUNCH_PRIO(ctx, st, prio_head, k_stage_transpose, grid, 256, 0, src, m, (int)blob_words, d.L.proof_words, d.L.query_words, d.Q, ws.pp,
+                        (u64 *)nullptr, d.L.proof_words);
+      }
     }
-    mark("k0_end", k, m, st);
+    mark("k0_end", k, m, pp_first ? side : st);
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     // K4 + K5 on the lane's side stream when the Merkle kernel runs in two phases: the leaf phase needs nothing from the
     // transcript, so the per-proof chains of K4/K5 (latency-bound, ~5 ms per chunk whatever its size) hide beside it.
@@ -480,17 +579,15 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
     // chunk's Merkle time: 379 k -> 397 k proofs/s end to end with the split; device-resident input, 25 k-proof chunks: the GPU
     // is saturated either way (the step is already within 2% of the sum of all kernels' work) and the second launch costs 1%
     // (436 k -> 431 k) — so the split follows the input.  P2V_SPLIT=0/1 forces it (A/B aid).
-    const bool split = (what & RUN_FRI) && (force_split >= 0 ? force_split == 1 : !src_dev);
-    cudaStream_t side = (split && depth >= 2) ? ctx->side_stream[lane] : st;
-    if (side != st) {
+    if (side != st && !pp_first) {
       P2V_CUDA(ctx, cudaEventRecord(ctx->staged_ev[lane], st));
       P2V_CUDA(ctx, cudaStreamWaitEvent(side, ctx->staged_ev[lane], 0));
     }
-    P2V_LAUNCH_ON(ctx, side, k_challenges, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
-    if (d.num_lookup_polys > 0) P2V_LAUNCH_ON(ctx, side, k_lookup_delta_copies, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m);
+    P2V_LAUNCH_PRIO(ctx, side, prio_head, k_challenges, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
+    if (d.num_lookup_polys > 0) P2V_LAUNCH_PRIO(ctx, side, prio_head, k_lookup_delta_copies, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m);
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     // K5
-    if (what & RUN_CONSTRAINTS) P2V_LAUNCH_ON(ctx, side, k_constraints, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
+    if (what & RUN_CONSTRAINTS) P2V_LAUNCH_PRIO(ctx, side, prio_head, k_constraints, (unsigned)((m + 127) / 128), 128, 0, d, ws, m);
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     if (side != st) P2V_CUDA(ctx, cudaEventRecord(ctx->transcript_ev[lane], side));
     mark("k5_end", k, m, side);
@@ -502,23 +599,24 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
       const bool pipe = depth >= 2;
       unsigned grid = pipe ? (unsigned)((items + P2V_MERKLE_BLOCK_PIPE - 1) / P2V_MERKLE_BLOCK_PIPE)
                            : (unsigned)p2v_grid_for(ctx, items, P2V_MERKLE_BLOCK, P2V_MERKLE_MINBLOCKS);
-#define P2V_MERKLE_LAUNCH(PHASE)                                                                                                                          \
-  do {                                                                                                                                                  \
-    if (pipe) P2V_LAUNCH_ON(ctx, st, (k_fri_merkle<P2V_MERKLE_BLOCK_PIPE, P2V_MERKLE_MINBLOCKS_PIPE, PHASE>), grid, P2V_MERKLE_BLOCK_PIPE, 0, d, ws, m); \
-    else P2V_LAUNCH_ON(ctx, st, (k_fri_merkle<P2V_MERKLE_BLOCK, P2V_MERKLE_MINBLOCKS, PHASE>), grid, P2V_MERKLE_BLOCK, 0, d, ws, m);                     \
+#define P2V_MERKLE_LAUNCH(PHASE, PRIO)                                                                                                                            \
+  do {                                                                                                                                                          \
+    if (pipe) P2V_LAUNCH_PRIO(ctx, st, PRIO, (k_fri_merkle<P2V_MERKLE_BLOCK_PIPE, P2V_MERKLE_MINBLOCKS_PIPE, PHASE>), grid, P2V_MERKLE_BLOCK_PIPE, 0, d, ws, m); \
+    else P2V_LAUNCH_ON(ctx, st, (k_fri_merkle<P2V_MERKLE_BLOCK, P2V_MERKLE_MINBLOCKS, PHASE>), grid, P2V_MERKLE_BLOCK, 0, d, ws, m);                             \
   } while (0)
       if (split) {
-        P2V_MERKLE_LAUNCH(MERKLE_LEAF);
+        P2V_MERKLE_LAUNCH(MERKLE_LEAF, prio_bulk);
         if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
         if (side != st) P2V_CUDA(ctx, cudaStreamWaitEvent(st, ctx->transcript_ev[lane], 0));
-        P2V_MERKLE_LAUNCH(MERKLE_PATH);
+        P2V_MERKLE_LAUNCH(MERKLE_PATH, prio_close);
       } else {
-        P2V_MERKLE_LAUNCH(MERKLE_ALL);
+        if (side != st) P2V_CUDA(ctx, cudaStreamWaitEvent(st, ctx->transcript_ev[lane], 0));
+        P2V_MERKLE_LAUNCH(MERKLE_ALL, prio_bulk);
         if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[7], st));
       }
 #undef P2V_MERKLE_LAUNCH
       if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[6], st));
-      P2V_LAUNCH_ON(ctx, st, k_fri_query, p2v_grid_for(ctx, m * d.Q, 256, 4), 256, 0, d, ws, m);
+      P2V_LAUNCH_PRIO(ctx, st, prio_close, k_fri_query, p2v_grid_for(ctx, m * d.Q, 256, 4), 256, 0, d, ws, m);
     } else if (side != st) {
       P2V_CUDA(ctx, cudaStreamWaitEvent(st, ctx->transcript_ev[lane], 0));
     }
@@ -527,7 +625,7 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
     if (out.verdict_mode) {
       u32 *stp = t.o_status.as<u32>() ? t.o_status.as<u32>() + c0 : nullptr;
       u32 *bits = t.o_bits.as<u32>() ? t.o_bits.as<u32>() + c0 / 32 : nullptr;
-      P2V_LAUNCH_ON(ctx, st, k_verdict, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m, out.verdict_mode, stp, bits);
+      P2V_LAUNCH_PRIO(ctx, st, prio_close, k_verdict, p2v_grid_for(ctx, m, 256, 8), 256, 0, d, ws, m, out.verdict_mode, stp, bits);
     }
     if (timed) P2V_CUDA(ctx, cudaEventRecord(ctx->ev[5], st));
     if (b >= 0) P2V_CUDA(ctx, cudaEventRecord(ctx->stage_free[b], st));  // K6a/K6b were the last readers of the chunk's blobs
@@ -539,6 +637,10 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
     if (t.o_qs.dev) P2V_LAUNCH_ON(ctx, st, k_copy_qstat, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.qstat, m, d.Q, t.o_qs.as<u32>(), c0);
     if (t.o_roots.dev) P2V_LAUNCH_ON(ctx, st, k_copy_roots, p2v_grid_for(ctx, m * d.Q * 4 * (4 + d.nsteps), 256, 8), 256, 0, ws.roots, m, d.Q, 4 + d.nsteps, t.o_roots.as<u64>(), n, c0);
     if (t.o_folded.dev) P2V_LAUNCH_ON(ctx, st, k_copy_folded, p2v_grid_for(ctx, m * d.Q, 256, 8), 256, 0, ws.folded, m, d.Q, t.o_folded.as<u64>(), n, c0);
+    if (pp_bytes) {
+      P2V_CUDA(ctx, cudaEventRecord(ctx->lane_done[lane], st));
+      lane_recorded[lane] = true;
+    }
   }
   if (depth >= 2) {
     // join: whoever orders work after us on the primary stream (D2H below, the caller's events, NCCL) sees all lanes

@@ -58,7 +58,9 @@ struct DevCircuit {
 // Per-chunk workspace planes
 struct Workspace {
   u64 *pp;     // [proof_words][n]
-  const u64 *aos;  // the chunk's blobs as they arrived, [n][blob_words]: the query parts are read in place
+  const u64 *aos;  // the chunk's query parts as they arrived: query part q of proof p starts at aos[p * aos_pitch + aos_qoff + q * query_words]
+  size_t aos_pitch;  // words per row: blob_words (whole blobs, device-resident input) or Q * query_words (host input: query parts only)
+  int aos_qoff;      // proof_words or 0
   u64 *ch;     // [ch_words][n]   challenges (canonical)
   u64 *pih;    // [4][n]          sponge(public_inputs)
   u64 *pre;    // [4][n]          precomputed reduced openings Y0, Y1 (Plonk/FRI.hs:128-134)
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(BLOCK, MINBLOCKS) k_fri_merkle(const __grid_co
     int q = (int)(rem / n);
     size_t p = rem - (size_t)q * n;
     // query part q of proof p, read in place: word w at qbase[w]
-    const u64 *__restrict__ qbase = ws.aos + p * (size_t)L.blob_words + L.proof_words + (size_t)q * L.query_words;
+    const u64 *__restrict__ qbase = ws.aos + p * ws.aos_pitch + ws.aos_qoff + (size_t)q * L.query_words;
     u32 index = PHASE == MERKLE_LEAF ? 0u : (u32)ws.ch[(size_t)(c.ch_idx + q) * n + p];  // the leaf phase must not touch K4's output
     int leaf_off, width, sib_off, plen, cap_off;
     if (tr < 4) {
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(256) k_fri_query(const __grid_constant__ DevCi
     int q = (int)(t / n);
     size_t p = t - (size_t)q * n;
     // query part q of proof p, read in place (word w at qbase[w]): a thread streams its own leaf values
-    const u64 *__restrict__ qbase = ws.aos + p * (size_t)L.blob_words + L.proof_words + (size_t)q * L.query_words;
+    const u64 *__restrict__ qbase = ws.aos + p * ws.aos_pitch + ws.aos_qoff + (size_t)q * L.query_words;
     u32 idx = (u32)ws.ch[(size_t)(c.ch_idx + q) * n + p];
     u32 init_bad = 0, step_bad = 0;
 #pragma unroll 1

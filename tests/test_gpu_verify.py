@@ -132,6 +132,36 @@ def test_ragged_batch_sizes(p2v, ctx, orc, n):
     assert tail == 0
 
 
+def test_host_transcript_first_windows(p2v, ctx, orc, monkeypatch):
+    """Host input on the pipeline copies the per-proof parts of a whole window of chunks first (strided), then the query parts
+    chunk by chunk.  Small windows (test hook P2V_PPFIRST_BYTES) force several of them, with a ragged last chunk; verdicts,
+    challenges and per-query results must equal the serial single-chunk run and the oracle."""
+    cir, shape, lay, vkey, blob = _circuit(p2v, ctx, "real5")
+    n = 64 * 11 + 19
+    blobs, words, deltas = fixtures.tampered_batch(blob, lay, shape, n, seed=33, accept_every=3)
+    ctx.set_pipeline(1)
+    acc0, st0 = cir.verifyProof(blobs)
+    ch0 = cir.proofChallenges(blobs)
+    st_f0, qs0, fold0 = cir.checkFRIProof(blobs, want_debug=True)
+    ctx.set_pipeline(p2v.DEFAULT_PIPELINE)
+    ctx.set_chunk(64)
+    try:
+        for win_chunks in (1, 3, 1000):
+            monkeypatch.setenv("P2V_PPFIRST_BYTES", str(lay.proof_words * 8 * 64 * win_chunks))
+            for depth in (2, 4):
+                ctx.set_pipeline(depth)
+                acc1, st1 = cir.verifyProof(blobs)
+                assert np.array_equal(st0, st1) and np.array_equal(acc0, acc1), (win_chunks, depth)
+            assert np.array_equal(ch0, cir.proofChallenges(blobs))
+            st_f1, qs1, fold1 = cir.checkFRIProof(blobs, want_debug=True)
+            assert np.array_equal(st_f0, st_f1) and np.array_equal(qs0, qs1) and np.array_equal(fold0, fold1)
+    finally:
+        ctx.set_chunk(0)
+        ctx.set_pipeline(p2v.DEFAULT_PIPELINE)
+    want = orc.verify_batch(shape, vkey, blobs, threads=4, fast=True)
+    assert np.array_equal(st0, want["status"])
+
+
 def test_host_ramped_pipeline_equals_device_resident(p2v, ctx, orc):
     """Host input with chunks >= 8192 takes the ramped multi-lane pipeline (chunk/8 growing x9/8): every proof must
     land in exactly one chunk.  Compared with the device-resident run of the same batch and, on a sample, the oracle."""
