@@ -324,6 +324,7 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
   // (stream + workspace each).  Device-resident input: ~3 GiB chunks.  Host input: ~0.5 GiB chunks — a chunk cannot start
   // before it has arrived and PCIe delivers proofs about as fast as the GPU verifies them, so there is never a backlog of
   // big chunks to overlap (tools/chunk_sweep.sh).
+  static const bool pp_first_on = !(getenv("P2V_PPFIRST") && atoi(getenv("P2V_PPFIRST")) == 0);  // transcript-first host schedule, see below
   std::vector<JobState> js(jobs.size());
   auto reject = [&](Job &j, int code, const std::string &msg) { j.rc = code; j.err = msg; };
   size_t total_chunks = 0;
@@ -338,7 +339,9 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
     t.src_dev = p2v_is_device_ptr(j.blobs);
     size_t chunk = ctx->chunk;
     if (chunk == 0) {
-      size_t budget = ctx->pipeline > 1 ? (t.src_dev ? ((size_t)3 << 30) : ((size_t)512 << 20)) : (t.src_dev ? ((size_t)16 << 30) : ((size_t)2 << 30));
+      // host input: 0.25 GiB with the transcript-first schedule (measured at 10^5 proofs, tools/e2e_chunk_tail.sh: 1056-proof chunks
+      // 373 k proofs/s, 2112: 425 k, 3200: 422 k, 4256: 419 k, 6400: 412 k), 0.5 GiB without it
+      size_t budget = ctx->pipeline > 1 ? (t.src_dev ? ((size_t)3 << 30) : ((size_t)(pp_first_on ? 256 : 512) << 20)) : (t.src_dev ? ((size_t)16 << 30) : ((size_t)2 << 30));
       chunk = budget / (t.blob_words * 8);
       if (chunk < 1024) chunk = 1024;
     }
@@ -373,7 +376,6 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
   // chunk by chunk (strided as well, so every byte still crosses PCIe once).  K0/K4/K5 of a chunk — a latency-bound chain of
   // 114 dependent permutations per proof, ~10 ms next to the Merkle blocks of other chunks — then run long before the chunk's
   // query parts arrive, and what is left after the LAST copy is the Merkle work of one short chunk instead of that chain.
-  static const bool pp_first_on = !(getenv("P2V_PPFIRST") && atoi(getenv("P2V_PPFIRST")) == 0);
   const size_t win_bytes = getenv("P2V_PPFIRST_BYTES") ? (size_t)atoll(getenv("P2V_PPFIRST_BYTES")) : ((size_t)1 << 30);  // test hook: small windows
   size_t pp_bytes = 0;
   if (pp_first_on && depth >= 2)
@@ -430,10 +432,11 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
   const bool timed = depth == 1;
   static const int force_split = getenv("P2V_SPLIT") ? atoi(getenv("P2V_SPLIT")) : -1;
   static const bool trace_on = getenv("P2V_TRACE") != nullptr;
-  // Launch priorities (P2V_PRIO: 0 = none, 1 = K0/K4/K5 first, 2 = also the closing kernels of a chunk before younger chunks' leaf
-  // blocks) and the tail of the host-input schedule (P2V_TAIL: the last chunk is halved repeatedly down to this many proofs)
+  // Launch priorities (P2V_PRIO: 0 = none (default), 1 = K0/K4/K5 first, 2 = also the closing kernels of a chunk before younger
+  // chunks' leaf blocks).  Measured at 10^5 proofs end to end: +1.3% with the chunk-by-chunk schedule (404 k -> 409 k proofs/s:
+  // K4's chain runs 11 ms instead of 22 ms next to the Merkle blocks), nothing with the transcript-first schedule, where K4 is
+  // off the critical path anyway; halving the last chunks (tail taper) changed nothing in either schedule and was removed.
   static const int prio_mode = getenv("P2V_PRIO") ? atoi(getenv("P2V_PRIO")) : 0;
-  static const size_t tail_min = getenv("P2V_TAIL") ? (size_t)atol(getenv("P2V_TAIL")) : 0;
   const int prio_head = prio_mode >= 1 ? ctx->prio_hi : 0;
   const int prio_close = prio_mode >= 2 ? std::min(ctx->prio_lo, ctx->prio_hi + 1) : 0;
   const int prio_bulk = prio_mode >= 1 ? ctx->prio_lo : 0;
@@ -470,13 +473,6 @@ int runJobs(p2v_ctx *ctx, std::vector<Job> &jobs, int what) {
         done += m;
         if (ramped) step = std::min(chunk, (step * P2V_RAMP_NUM / P2V_RAMP_DEN + 31) / 32 * 32);
       }
-      // tail: what is left when the last copy ends is the whole latency of the last chunk — make the last chunks short
-      if (!src_dev && depth >= 2 && tail_min >= 32)
-        while (sizes.back() >= 2 * tail_min) {
-          size_t last = sizes.back(), half = (last / 2 + 31) / 32 * 32;
-          sizes.back() = half;
-          sizes.push_back(last - half);
-        }
     }
     size_t c0 = 0, win_left = 0;
     for (size_t i = 0; i < sizes.size(); i++) {
