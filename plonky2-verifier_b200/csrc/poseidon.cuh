@@ -530,9 +530,53 @@ __device__ __forceinline__ void poseidon_mds_crt64(u64 (&s)[12], int next_round)
 #define POSEIDON_CRT_LEVEL2 1
 #endif
 #ifndef POSEIDON_FUSE_SBOX
-#define POSEIDON_FUSE_SBOX 1 /* 1: full rounds hand the last product of x^7 to the layer unreduced; 2: partial rounds too */
+#define POSEIDON_FUSE_SBOX 1 /* full rounds hand the last product of x^7 to the layer unreduced (in partial rounds it measured 1% slower) */
 #endif
 #if POSEIDON_CRT_LEVEL2
+// Equivalent round constants (POSEIDON_EQUIV_RC).  In a partial round only lane 0 goes through the s-box, so the constants of lanes
+// 1..11 commute with it and can be pushed through the linear layer into the next round's constants:
+//     M S(u) = M S(u - d) + M d      for d with d_0 = 0            (S = x^7 on lane 0, identity elsewhere)
+// Rounds 5..25 are left with a constant on lane 0 only; what has been pushed along arrives, as a full vector, in the constants of
+// round 26 (the first of the closing full rounds).  The state between rounds differs from the textbook one, the result of the
+// permutation does not.  The point: 18 of the 24 seeds of a partial-round layer become the same in every round, so they are
+// compile-time addresses in the constant bank (operands) instead of 18 indexed uniform loads per round.
+struct PoseidonEquivRc {
+  u64 v[31][12];
+};
+constexpr u64 poseidon_mulsmall_c(u64 x, u32 c) {  // x < p
+  u64 r = 0, t = x;
+  for (; c; c >>= 1) {
+    if (c & 1) r = poseidon_addmod_c(r, t);
+    t = poseidon_addmod_c(t, t);
+  }
+  return r;
+}
+constexpr PoseidonEquivRc poseidon_make_equiv_rc(bool push) {
+  constexpr u64 rc[360] = P2V_ALL_ROUND_CONSTANTS;
+  constexpr u32 circ[12] = POSEIDON_MDS_ROW;
+  PoseidonEquivRc t{};
+  u64 d[12] = {};  // what the previous round pushed forward (lane 0 = 0)
+  for (int r = 0; r < 30; r++) {
+    u64 v[12] = {};
+    for (int i = 0; i < 12; i++) {
+      u64 x = rc[r * 12 + i];
+      if (x >= GL_P) x -= GL_P;
+      u64 md = 0;  // (M d)_i
+      for (int j = 1; j < 12; j++) md = poseidon_addmod_c(md, poseidon_mulsmall_c(d[j], circ[(j - i + 12) % 12]));
+      v[i] = poseidon_addmod_c(x, md);
+    }
+    const bool strip = push && r >= 5 && r <= 25;
+    for (int i = 0; i < 12; i++) {
+      t.v[r][i] = (strip && i > 0) ? 0 : v[i];
+      d[i] = (strip && i > 0) ? v[i] : 0;
+    }
+  }
+  return t;
+}
+#ifndef POSEIDON_EQUIV_RC
+#define POSEIDON_EQUIV_RC 1
+#endif
+
 // one 16-byte aligned row of 24 seeds per round, in the order they are consumed (ptxas fetches them with 128-bit uniform loads):
 // [0..5] D' low, [6..11] D' high, [12..14] e low, [15..17] g low, [18..20] e high, [21..23] g high
 struct alignas(16) PoseidonRcCrt64L2 {
@@ -540,16 +584,14 @@ struct alignas(16) PoseidonRcCrt64L2 {
 };
 enum { L2_DL = 0, L2_DH = 6, L2_EL = 12, L2_GL = 15, L2_EH = 18, L2_GH = 21 };
 constexpr PoseidonRcCrt64L2 poseidon_make_rc_crt64_l2() {
-  constexpr u64 rc[360] = P2V_ALL_ROUND_CONSTANTS;
+  constexpr PoseidonEquivRc rce = poseidon_make_equiv_rc(POSEIDON_EQUIV_RC != 0);
   constexpr u64 kadj = ((u64)P2V_F64_K << 33) - (u64)P2V_F64_K;
   constexpr u64 cadj = GL_P - kadj;
   PoseidonRcCrt64L2 t{};
   for (int r = 0; r < 31; r++) {
     u64 alo[6] = {}, ahi[6] = {}, blo[6] = {}, bhi[6] = {};
     for (int i = 0; i < 6; i++) {
-      u64 ra = r < 30 ? rc[r * 12 + i] : 0, rb = r < 30 ? rc[r * 12 + i + 6] : 0;
-      if (ra >= GL_P) ra -= GL_P;
-      if (rb >= GL_P) rb -= GL_P;
+      u64 ra = rce.v[r][i], rb = rce.v[r][i + 6];  // canonical; row 30 is zero
       u64 a = poseidon_addmod_c(ra, cadj), b = poseidon_addmod_c(rb, cadj);
       alo[i] = a & 0xFFFFFFFFULL; ahi[i] = a >> 32; blo[i] = b & 0xFFFFFFFFULL; bhi[i] = b >> 32;
 #if POSEIDON_FUSE_SBOX
@@ -568,12 +610,13 @@ constexpr PoseidonRcCrt64L2 poseidon_make_rc_crt64_l2() {
       }
     }
     for (int i = 0; i < 3; i++) {
-      // sigma = (a + b) / 2 per part; make sigma_i + sigma_{i+3} even in both parts by moving a_{i+3} (all increments even)
+      // sigma = (a + b) / 2 per part; make sigma_i + sigma_{i+3} even in both parts by moving a_i (all increments even).  a_i, not
+      // a_{i+3}: with equivalent constants only lane 0 differs from round to round, and so must everything derived from it
       bool olo = (((alo[i] + blo[i]) / 2 + (alo[i + 3] + blo[i + 3]) / 2) & 1) != 0;
       bool ohi = (((ahi[i] + bhi[i]) / 2 + (ahi[i + 3] + bhi[i + 3]) / 2) & 1) != 0;
-      if (olo && ohi) { alo[i + 3] += 2; ahi[i + 3] += (1ULL << 33) - 2; }                        // + 2p
-      else if (olo) { alo[i + 3] += 2 + (1ULL << 33); ahi[i + 3] += (1ULL << 33) - 4; }          // + 2p, 2^33 moved down
-      else if (ohi) { alo[i + 3] += 4 + (1ULL << 33); ahi[i + 3] += (1ULL << 34) - 6; }          // both of the above
+      if (olo && ohi) { alo[i] += 2; ahi[i] += (1ULL << 33) - 2; }                        // + 2p
+      else if (olo) { alo[i] += 2 + (1ULL << 33); ahi[i] += (1ULL << 33) - 4; }          // + 2p, 2^33 moved down
+      else if (ohi) { alo[i] += 4 + (1ULL << 33); ahi[i] += (1ULL << 34) - 6; }          // both of the above
     }
     for (int i = 0; i < 6; i++) {
       t.v[r][L2_DL + i] = (double)(((long long)alo[i] - (long long)blo[i]) / 2);
@@ -591,6 +634,28 @@ constexpr PoseidonRcCrt64L2 poseidon_make_rc_crt64_l2() {
   return t;
 }
 static __constant__ PoseidonRcCrt64L2 c_rc64l2 = poseidon_make_rc_crt64_l2();
+#if POSEIDON_EQUIV_RC
+// rows 5..25 (the layers of rounds 4..24) differ only in the six seeds that lane 0 reaches: D'_0, e_0, g_0 of either part
+__host__ __device__ constexpr bool poseidon_l2_seed_varies(int k) { return k == L2_DL || k == L2_DH || k == L2_EL || k == L2_GL || k == L2_EH || k == L2_GH; }
+struct alignas(16) PoseidonRcL2Static {
+  double v[24];
+};
+constexpr PoseidonRcL2Static poseidon_make_rc_l2_static() {
+  constexpr PoseidonRcCrt64L2 t = poseidon_make_rc_crt64_l2();
+  PoseidonRcL2Static r{};
+  for (int k = 0; k < 24; k++) r.v[k] = t.v[5][k];
+  return r;
+}
+constexpr bool poseidon_l2_static_ok() {
+  constexpr PoseidonRcCrt64L2 t = poseidon_make_rc_crt64_l2();
+  for (int r = 5; r <= 25; r++)
+    for (int k = 0; k < 24; k++)
+      if (!poseidon_l2_seed_varies(k) && t.v[r][k] != t.v[5][k]) return false;
+  return true;
+}
+static_assert(poseidon_l2_static_ok(), "partial-round seeds that lane 0 does not reach must not depend on the round");
+static __constant__ PoseidonRcL2Static c_l2s = poseidon_make_rc_l2_static();
+#endif
 
 // pair J: conversions, butterfly, the D' half accumulated at once (column-major), X+ kept for the second level
 template <int J, int I>
@@ -644,29 +709,39 @@ __device__ __forceinline__ void poseidon_l2_s(const double (&X)[6], const double
   S[1] = fma(E1, 16.0, SD1); S[4] = fma(E1, 16.0, -SD1);
   S[2] = fma(E2, 16.0, SD2); S[5] = fma(E2, 16.0, -SD2);
 }
-__device__ __forceinline__ void poseidon_l2_seed_d(double (&DL)[6], double (&DH)[6], int next_round) {
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-    DL[i] = c_rc64l2.v[next_round][L2_DL + i];
-    DH[i] = c_rc64l2.v[next_round][L2_DH + i];
-  }
+// ST: a partial round whose layer adds a constant on lane 0 only (rows 5..25 with equivalent constants): all seeds but six come
+// from compile-time addresses
+template <bool ST, int K>
+__device__ __forceinline__ double poseidon_l2_seed(int next_round) {
+#if POSEIDON_EQUIV_RC
+  if constexpr (ST && !poseidon_l2_seed_varies(K)) return c_l2s.v[K];
+#endif
+  return c_rc64l2.v[next_round][K];
 }
+template <bool ST = false>
+__device__ __forceinline__ void poseidon_l2_seed_d(double (&DL)[6], double (&DH)[6], int next_round) {
+  DL[0] = poseidon_l2_seed<ST, L2_DL + 0>(next_round); DH[0] = poseidon_l2_seed<ST, L2_DH + 0>(next_round);
+  DL[1] = poseidon_l2_seed<ST, L2_DL + 1>(next_round); DH[1] = poseidon_l2_seed<ST, L2_DH + 1>(next_round);
+  DL[2] = poseidon_l2_seed<ST, L2_DL + 2>(next_round); DH[2] = poseidon_l2_seed<ST, L2_DH + 2>(next_round);
+  DL[3] = poseidon_l2_seed<ST, L2_DL + 3>(next_round); DH[3] = poseidon_l2_seed<ST, L2_DH + 3>(next_round);
+  DL[4] = poseidon_l2_seed<ST, L2_DL + 4>(next_round); DH[4] = poseidon_l2_seed<ST, L2_DH + 4>(next_round);
+  DL[5] = poseidon_l2_seed<ST, L2_DL + 5>(next_round); DH[5] = poseidon_l2_seed<ST, L2_DH + 5>(next_round);
+}
+template <bool ST = false>
 __device__ __forceinline__ void poseidon_l2_sums(const double (&XL)[6], const double (&XH)[6], int next_round, double (&SL)[6], double (&SH)[6]) {
   double el[3], gl[3], eh[3], gh[3];
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    el[i] = c_rc64l2.v[next_round][L2_EL + i];
-    gl[i] = c_rc64l2.v[next_round][L2_GL + i];
-    eh[i] = c_rc64l2.v[next_round][L2_EH + i];
-    gh[i] = c_rc64l2.v[next_round][L2_GH + i];
-  }
+  el[0] = poseidon_l2_seed<ST, L2_EL + 0>(next_round); el[1] = poseidon_l2_seed<ST, L2_EL + 1>(next_round); el[2] = poseidon_l2_seed<ST, L2_EL + 2>(next_round);
+  gl[0] = poseidon_l2_seed<ST, L2_GL + 0>(next_round); gl[1] = poseidon_l2_seed<ST, L2_GL + 1>(next_round); gl[2] = poseidon_l2_seed<ST, L2_GL + 2>(next_round);
+  eh[0] = poseidon_l2_seed<ST, L2_EH + 0>(next_round); eh[1] = poseidon_l2_seed<ST, L2_EH + 1>(next_round); eh[2] = poseidon_l2_seed<ST, L2_EH + 2>(next_round);
+  gh[0] = poseidon_l2_seed<ST, L2_GH + 0>(next_round); gh[1] = poseidon_l2_seed<ST, L2_GH + 1>(next_round); gh[2] = poseidon_l2_seed<ST, L2_GH + 2>(next_round);
   poseidon_l2_s(XL, el, gl, SL);
   poseidon_l2_s(XH, eh, gh, SH);
 }
+template <bool ST = false>
 __device__ __forceinline__ void poseidon_l2_finish(u64 (&s)[12], u64 x0, const double (&XL)[6], const double (&XH)[6], const double (&DL)[6],
                                                    const double (&DH)[6], int next_round) {
   double SL[6], SH[6];
-  poseidon_l2_sums(XL, XH, next_round, SL, SH);
+  poseidon_l2_sums<ST>(XL, XH, next_round, SL, SH);
   poseidon_crt64_finish(s, x0, SL, DL, SH, DH);
 }
 // lane 0 given as its two parts (fused s-box)
@@ -676,33 +751,18 @@ __device__ __forceinline__ void poseidon_l2_finish_d(u64 (&s)[12], double l0, do
   poseidon_l2_sums(XL, XH, next_round, SL, SH);
   poseidon_crt64_finish_d(s, l0, h0, SL, DL, SH, DH);
 }
+template <bool ST = false>
 __device__ __forceinline__ void poseidon_mds_crt64_l2(u64 (&s)[12], int next_round) {
   double XL[6], XH[6], DL[6], DH[6];
-  poseidon_l2_seed_d(DL, DH, next_round);
+  poseidon_l2_seed_d<ST>(DL, DH, next_round);
   poseidon_l2_pair<1>(s[1], s[7], XL, XH, DL, DH);
   poseidon_l2_pair<2>(s[2], s[8], XL, XH, DL, DH);
   poseidon_l2_pair<3>(s[3], s[9], XL, XH, DL, DH);
   poseidon_l2_pair<4>(s[4], s[10], XL, XH, DL, DH);
   poseidon_l2_pair<5>(s[5], s[11], XL, XH, DL, DH);
   poseidon_l2_pair<0>(s[0], s[6], XL, XH, DL, DH);
-  poseidon_l2_finish(s, s[0], XL, XH, DL, DH, next_round);
+  poseidon_l2_finish<ST>(s, s[0], XL, XH, DL, DH, next_round);
 }
-#if POSEIDON_FUSE_SBOX >= 2
-// partial round with the s-box of lane 0 fused into the layer
-__device__ __forceinline__ void poseidon_partial_round_crt64_l2(u64 (&s)[12], int next_round) {
-  double XL[6], XH[6], DL[6], DH[6];
-  poseidon_l2_seed_d(DL, DH, next_round);
-  poseidon_l2_pair<1>(s[1], s[7], XL, XH, DL, DH);
-  poseidon_l2_pair<2>(s[2], s[8], XL, XH, DL, DH);
-  poseidon_l2_pair<3>(s[3], s[9], XL, XH, DL, DH);
-  poseidon_l2_pair<4>(s[4], s[10], XL, XH, DL, DH);
-  poseidon_l2_pair<5>(s[5], s[11], XL, XH, DL, DH);
-  double l0, h0;
-  poseidon_sbox_raw(s[0], l0, h0);
-  poseidon_l2_pair_d<0>(l0, h0, __uint2double_rn((u32)s[6]), __uint2double_rn((u32)(s[6] >> 32)), XL, XH, DL, DH);
-  poseidon_l2_finish_d(s, l0, h0, XL, XH, DL, DH, next_round);
-}
-#endif
 __device__ __forceinline__ void poseidon_full_round_crt64_l2(u64 (&s)[12], int next_round) {
   double XL[6], XH[6], DL[6], DH[6];
   poseidon_l2_seed_d(DL, DH, next_round);
@@ -777,9 +837,22 @@ __device__ __forceinline__ void poseidon_mds_layer(u64 (&s)[12], int next_round)
   poseidon_mds(s, next_round);
 #endif
 }
+// a + c for a CANONICAL constant c (< p), a lazy: after a wrap the low word is a + c - 2^64 <= p - 2, so the single correction
+// + EPS cannot wrap again — 5 instructions against the 12 of gl_add with its two possible wraps
+constexpr bool poseidon_rc_canonical() {
+  constexpr u64 rc[360] = P2V_ALL_ROUND_CONSTANTS;
+  for (int i = 0; i < 360; i++)
+    if (rc[i] >= GL_P) return false;
+  return true;
+}
+static_assert(poseidon_rc_canonical(), "round constants must be canonical");
+__device__ __forceinline__ u64 poseidon_add_rc(u64 a, u64 c) {
+  u64 r = a + c;
+  return r < a ? r + GL_EPS : r;
+}
 __device__ __forceinline__ void poseidon_permute(u64 (&s)[12]) {
 #pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], c_pt.rc[0][i]);
+  for (int i = 0; i < 12; i++) s[i] = poseidon_add_rc(s[i], c_pt.rc[0][i]);
 #if POSEIDON_SPLIT_ROUNDS
   // Two loop bodies instead of one with a branch: a full round (12 s-boxes + layer in one basic block, so that the layer's
   // FP64/ALU work is scheduled into the shadow of the wide multiplies) and a partial round.
@@ -800,15 +873,22 @@ __device__ __forceinline__ void poseidon_permute(u64 (&s)[12]) {
 #endif
       }
     } else {
+#if POSEIDON_MDS_F64 == 4 && POSEIDON_CRT_LEVEL2 && POSEIDON_EQUIV_RC
+      // rounds 4..24 add a constant on lane 0 only (equivalent constants); round 25 hands the full vector on to the closing rounds
+#pragma unroll 1
+      for (int r = 4; r < 25; r++) {
+        s[0] = poseidon_sbox(s[0]);
+        poseidon_mds_crt64_l2<true>(s, r + 1);
+      }
+      s[0] = poseidon_sbox(s[0]);
+      poseidon_mds_crt64_l2<false>(s, 26);
+#else
 #pragma unroll 1
       for (int r = 4; r < 26; r++) {
-#if POSEIDON_MDS_F64 == 4 && POSEIDON_CRT_LEVEL2 && POSEIDON_FUSE_SBOX >= 2
-        poseidon_partial_round_crt64_l2(s, r + 1);
-#else
         s[0] = poseidon_sbox(s[0]);
         poseidon_mds_layer(s, r + 1);
-#endif
       }
+#endif
     }
   }
 #else
