@@ -303,12 +303,13 @@ __global__ void __launch_bounds__(128) k_challenges(const __grid_constant__ DevC
 #endif
 // Two instantiations: BLOCK = P2V_MERKLE_BLOCK for a kernel that has the GPU to itself (serial mode), and
 // P2V_MERKLE_BLOCK_PIPE for the chunk pipeline, where blocks of several lanes' kernels share the SMs: 128-thread
-// blocks at 5 per SM (96 registers) interleave better there (+1% throughput) although the kernel alone is 1.5% slower.
+// blocks interleave better there.  Round 1: 5 per SM (96 registers) +1% over 256 x 2.  Round 2, after the equivalent-constant
+// partial rounds (10^5 device-resident proofs): 128 x 5 481 k proofs/s, 192 x 4 485 k, 256 x 3 486 k, 128 x 6 (80 registers) 487 k.
 #ifndef P2V_MERKLE_BLOCK_PIPE
 #define P2V_MERKLE_BLOCK_PIPE 128
 #endif
 #ifndef P2V_MERKLE_MINBLOCKS_PIPE
-#define P2V_MERKLE_MINBLOCKS_PIPE 5
+#define P2V_MERKLE_MINBLOCKS_PIPE 6
 #endif
 // PHASE: the kernel runs in two launches per chunk.  The leaf sponges (43% of the permutations at the standard shape)
 // need nothing from the transcript, so PHASE 1 starts right after K0 while K4/K5 of the same chunk — one thread per proof,

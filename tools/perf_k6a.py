@@ -29,6 +29,8 @@ ppq = sum(c8(lay.oracle_width[o]) + lay.init_path_len for o in range(4)) + sum(c
 perms = n * shape.num_queries * ppq
 pps = perms / (ms["fri_merkle"] * 1e-3)
 ctx.set_pipeline(p2v.DEFAULT_PIPELINE)
+if os.environ.get("P2V_PERF_CHUNK"):  # several chunks even for a small batch, so that the pipelined instantiation is what launches (profiles)
+    ctx.set_chunk(int(os.environ["P2V_PERF_CHUNK"]))
 st = torch.cuda.ExternalStream(ctx.stream)
 for _ in range(2):
     cir.verifyProof(d_blobs, n=n, accept_bits=bits, status=status)

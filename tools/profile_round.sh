@@ -9,7 +9,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 # serial instantiation (what roofline.frac times): the pipeline-depth-1 pass of perf_k6a.py
 ncu --set full --import-source on --clock-control none -k regex:k_fri_merkle -s 0 -c 1 -f -o gpurun_out/${R}_k_fri_merkle_serial \
     python tools/perf_k6a.py 16384 > gpurun_out/${R}_ncu_full_serial.log 2>&1
-# pipelined instantiation (what the timed region launches): skip the two serial launches
-ncu --set full --import-source on --clock-control none -k regex:k_fri_merkle -s 2 -c 1 -f -o gpurun_out/${R}_k_fri_merkle_pipe \
+# pipelined instantiation (what the timed region launches): skip the two serial launches; two chunks of 8192 proofs, so that the
+# call takes the multi-lane path (one chunk would run the serial instantiation again)
+P2V_PERF_CHUNK=8192 ncu --set full --import-source on --clock-control none -k regex:k_fri_merkle -s 2 -c 1 -f -o gpurun_out/${R}_k_fri_merkle_pipe \
     python tools/perf_k6a.py 16384 > gpurun_out/${R}_ncu_full_pipe.log 2>&1
 tail -2 gpurun_out/${R}_ncu_full_serial.log gpurun_out/${R}_ncu_full_pipe.log
