@@ -389,7 +389,7 @@ __device__ __forceinline__ void poseidon_mds_crt(u64 (&s)[12], int next_round) {
 struct PoseidonRcCrt64 {
   double sl[31][6], dl[31][6], sh[31][6], dh[31][6];
 };
-constexpr u64 poseidon_addmod_c(u64 a, u64 b) {  // a, b < p
+__host__ __device__ constexpr u64 poseidon_addmod_c(u64 a, u64 b) {  // a, b < p
   u64 r = a + b;
   return (r < a || r >= GL_P) ? r - GL_P : r;
 }
@@ -543,7 +543,7 @@ __device__ __forceinline__ void poseidon_mds_crt64(u64 (&s)[12], int next_round)
 struct PoseidonEquivRc {
   u64 v[31][12];
 };
-constexpr u64 poseidon_mulsmall_c(u64 x, u32 c) {  // x < p
+__host__ __device__ constexpr u64 poseidon_mulsmall_c(u64 x, u32 c) {  // x < p
   u64 r = 0, t = x;
   for (; c; c >>= 1) {
     if (c & 1) r = poseidon_addmod_c(r, t);
@@ -551,7 +551,7 @@ constexpr u64 poseidon_mulsmall_c(u64 x, u32 c) {  // x < p
   }
   return r;
 }
-constexpr PoseidonEquivRc poseidon_make_equiv_rc(bool push) {
+__host__ __device__ constexpr PoseidonEquivRc poseidon_make_equiv_rc(bool push) {
   constexpr u64 rc[360] = P2V_ALL_ROUND_CONSTANTS;
   constexpr u32 circ[12] = POSEIDON_MDS_ROW;
   PoseidonEquivRc t{};
@@ -794,6 +794,185 @@ __device__ __forceinline__ void poseidon_full_round_crt64_l2(u64 (&s)[12], int n
 }
 #endif
 
+// ---- two partial rounds as ONE layer (POSEIDON_DOUBLE_ROUNDS) ------------------------------------------------------------
+// In a partial round eleven of the twelve lanes only pass through the linear layer, so two consecutive partial rounds are one
+// application of M^2 plus a rank-one correction for the s-box in between.  With v = (x_r, s_1..s_11), x_r = sbox(s_0), C = circ(c),
+// M = C + 8 E00, t0 = (M v)_0 (ONE row of the first layer), x' = sbox(t0 + const) the s-box of the second round:
+//     M (x', (M v)_1..11) = M^2 v + col0(M) (x' - t0),      M^2 v = C^2 v + 8 x_r col0(C) + 8 t0 e_0
+//     =>  state after both rounds = C^2 v + col0(C) w + 8 x' e_0 (+ constants),     w = 8 x_r + x' - t0.
+// C^2 = circ(c * c) goes through the same CRT butterfly as C (its coefficients sum to 2^16: word sums < 2^49, exact), col0(C) w
+// is the contribution of a thirteenth input to the SINGLE layer's sums, and t0 costs 12 multiply-adds per part: 248 FP64
+// operations for two rounds instead of 360, one set of conversions and folds instead of two.  Every coefficient that reaches an
+// output is non-negative (c*c >= 4586 > 41 * 41 + ...), so only the unreduced low part of x' needs the 2^42 lift of the fused
+// s-box.  Needs the equivalent round constants: the middle round adds a constant on lane 0 only.
+#ifndef POSEIDON_DOUBLE_ROUNDS
+#define POSEIDON_DOUBLE_ROUNDS 1
+#endif
+#if POSEIDON_DOUBLE_ROUNDS && POSEIDON_EQUIV_RC && POSEIDON_CRT_LEVEL2 && POSEIDON_FUSE_SBOX
+struct PoseidonSqCoef {
+  int p2h[6], q2h[6];  // halved CRT coefficients of c * c (cyclic): (c2_d + c2_{d+6}) / 2, (c2_d - c2_{d+6}) / 2
+  int m0[12];          // row 0 of M
+};
+__host__ __device__ constexpr PoseidonSqCoef poseidon_make_sq_coef() {
+  constexpr int c[12] = POSEIDON_MDS_ROW;
+  PoseidonSqCoef t{};
+  int c2[12] = {};
+  for (int k = 0; k < 12; k++)
+    for (int j = 0; j < 12; j++) c2[k] += c[j] * c[(k - j + 12) % 12];
+  for (int d = 0; d < 6; d++) {
+    t.p2h[d] = (c2[d] + c2[d + 6]) / 2;
+    t.q2h[d] = (c2[d] - c2[d + 6]) / 2;
+  }
+  for (int j = 0; j < 12; j++) t.m0[j] = c[j] + (j == 0 ? 8 : 0);
+  return t;
+}
+constexpr bool poseidon_sq_coef_ok() {
+  constexpr int c[12] = POSEIDON_MDS_ROW;
+  constexpr PoseidonSqCoef t = poseidon_make_sq_coef();
+  int c2[12] = {};
+  for (int k = 0; k < 12; k++)
+    for (int j = 0; j < 12; j++) c2[k] += c[j] * c[(k - j + 12) % 12];
+  for (int d = 0; d < 6; d++)
+    if ((c2[d] + c2[d + 6]) % 2 || (c2[d] - c2[d + 6]) % 2) return false;
+  // every net coefficient of an input word in an output word is >= 0:  c2[(j-i)] - C[i][0] m0[j] (+ 8 C[i][0] for j = 0)
+  for (int i = 0; i < 12; i++)
+    for (int j = 0; j < 12; j++)
+      if (c2[(j - i + 12) % 12] - c[(12 - i) % 12] * t.m0[j] + (j == 0 ? 8 * c[(12 - i) % 12] : 0) < 0) return false;
+  return true;
+}
+static_assert(poseidon_sq_coef_ok(), "double partial rounds: coefficient conditions");
+
+// seeds of double round k (rounds 4 + 2k and 5 + 2k): [0..5] S low, [6..11] D low, [12..17] S high, [18..23] D high for the
+// constants of round 6 + 2k, then the two parts of the seed of t0 (lane-0 constant of round 5 + 2k)
+struct alignas(16) PoseidonRcDbl {
+  double v[11][26];
+};
+enum { DBL_SL = 0, DBL_DL = 6, DBL_SH = 12, DBL_DH = 18, DBL_TL = 24, DBL_TH = 25 };
+__host__ __device__ constexpr PoseidonRcDbl poseidon_make_rc_dbl() {
+  constexpr PoseidonEquivRc rce = poseidon_make_equiv_rc(true);
+  constexpr u64 kadj = ((u64)P2V_F64_K << 33) - (u64)P2V_F64_K;
+  constexpr u64 cadj = GL_P - kadj;
+  PoseidonRcDbl t{};
+  for (int k = 0; k < 11; k++) {
+    const int r1 = 5 + 2 * k, r2 = 6 + 2 * k;
+    for (int i = 0; i < 6; i++) {
+      u64 a = poseidon_addmod_c(rce.v[r2][i], cadj), b = poseidon_addmod_c(rce.v[r2][i + 6], cadj);
+      u64 alo = a & 0xFFFFFFFFULL, ahi = a >> 32, blo = b & 0xFFFFFFFFULL, bhi = b >> 32;
+      // the unreduced low part of x' is in (-2^34, 2^32) and reaches every output with a coefficient <= 49: lift the low parts by
+      // 2^42, take 2^10 off the high parts (same value); a high part below 2^10 is first moved up by p
+      if (ahi < 1024) { alo += 1; ahi += 0xFFFFFFFFULL; }
+      if (bhi < 1024) { blo += 1; bhi += 0xFFFFFFFFULL; }
+      alo += 1ULL << 42; blo += 1ULL << 42; ahi -= 1024; bhi -= 1024;
+      bool flo = ((alo ^ blo) & 1) != 0, fhi = ((ahi ^ bhi) & 1) != 0;
+      if (flo && fhi) { blo += 1; bhi += 0xFFFFFFFFULL; }
+      else if (flo) { blo += 1 + (1ULL << 32); bhi += 0xFFFFFFFEULL; }
+      else if (fhi) { blo += 1ULL << 32; bhi -= 1; }
+      t.v[k][DBL_SL + i] = P2V_TWO52 + (double)((alo + blo) / 2);
+      t.v[k][DBL_DL + i] = (double)(((long long)alo - (long long)blo) / 2);
+      t.v[k][DBL_SH + i] = P2V_TWO52 + (double)((ahi + bhi) / 2);
+      t.v[k][DBL_DH + i] = (double)(((long long)ahi - (long long)bhi) / 2);
+    }
+    u64 a = poseidon_addmod_c(rce.v[r1][0], cadj);
+    t.v[k][DBL_TL] = P2V_TWO52 + (double)(a & 0xFFFFFFFFULL);
+    t.v[k][DBL_TH] = P2V_TWO52 + (double)(a >> 32);
+  }
+  return t;
+}
+__host__ __device__ constexpr bool poseidon_dbl_seed_varies(int k) { return k == DBL_SL || k == DBL_DL || k == DBL_SH || k == DBL_DH || k >= DBL_TL; }
+constexpr bool poseidon_dbl_static_ok() {
+  constexpr PoseidonRcDbl t = poseidon_make_rc_dbl();
+  constexpr PoseidonEquivRc rce = poseidon_make_equiv_rc(true);
+  for (int k = 0; k < 10; k++)
+    for (int j = 0; j < 26; j++)
+      if (!poseidon_dbl_seed_varies(j) && t.v[k][j] != t.v[0][j]) return false;
+  for (int r = 5; r <= 25; r++)  // the middle rounds (and all but the last target) carry a constant on lane 0 only
+    for (int i = 1; i < 12; i++)
+      if (rce.v[r][i] != 0) return false;
+  return true;
+}
+static_assert(poseidon_dbl_static_ok(), "double partial rounds: seeds that lane 0 does not reach must not depend on the round");
+static __constant__ PoseidonRcDbl c_rcdbl = poseidon_make_rc_dbl();
+struct alignas(16) PoseidonRcDblStatic {
+  double v[24];
+};
+__host__ __device__ constexpr PoseidonRcDblStatic poseidon_make_rc_dbl_static() {
+  constexpr PoseidonRcDbl t = poseidon_make_rc_dbl();
+  PoseidonRcDblStatic r{};
+  for (int j = 0; j < 24; j++) r.v[j] = t.v[0][j];
+  return r;
+}
+
+// the round-independent seeds as compile-time values: ten of the D seeds are zero (a multiply instead of a multiply-add), the ten
+// S seeds are one value per part
+constexpr PoseidonRcDblStatic k_rcdbls = poseidon_make_rc_dbl_static();
+template <bool ST, int K>
+__device__ __forceinline__ double poseidon_dbl_seed(int k) {
+  if constexpr (ST && !poseidon_dbl_seed_varies(K)) {
+    constexpr double v = k_rcdbls.v[K];
+    return v;
+  }
+  return c_rcdbl.v[k][K];
+}
+// contribution of input pair J to the C^2 sums of rows I..5
+template <int J, int I>
+__device__ __forceinline__ void poseidon_dbl_col(double (&SL)[6], double (&DL)[6], double (&SH)[6], double (&DH)[6], double xpL, double xmL, double xpH,
+                                                 double xmH) {
+  constexpr PoseidonSqCoef cf = poseidon_make_sq_coef();
+  constexpr int d = (J - I + 12) % 12;
+  constexpr double pc = (double)cf.p2h[d % 6];
+  constexpr double qc = (double)(d < 6 ? cf.q2h[d] : -cf.q2h[d - 6]);
+  SL[I] = fma(xpL, pc, SL[I]);
+  DL[I] = fma(xmL, qc, DL[I]);
+  SH[I] = fma(xpH, pc, SH[I]);
+  DH[I] = fma(xmH, qc, DH[I]);
+  if constexpr (I + 1 < 6) poseidon_dbl_col<J, I + 1>(SL, DL, SH, DH, xpL, xmL, xpH, xmH);
+}
+// pair (v_J, v_{J+6}): conversions, its share of t0, butterfly, C^2 sums
+template <int J>
+__device__ __forceinline__ void poseidon_dbl_pair(u64 xj, u64 xk, double &tL, double &tH, double (&SL)[6], double (&DL)[6], double (&SH)[6],
+                                                  double (&DH)[6]) {
+  constexpr PoseidonSqCoef cf = poseidon_make_sq_coef();
+  double bjl = __uint2double_rn((u32)xj), bjh = __uint2double_rn((u32)(xj >> 32));
+  double bkl = __uint2double_rn((u32)xk), bkh = __uint2double_rn((u32)(xk >> 32));
+  tL = fma(bjl, (double)cf.m0[J], tL);
+  tH = fma(bjh, (double)cf.m0[J], tH);
+  tL = fma(bkl, (double)cf.m0[J + 6], tL);
+  tH = fma(bkh, (double)cf.m0[J + 6], tH);
+  poseidon_dbl_col<J, 0>(SL, DL, SH, DH, bjl + bkl, bjl - bkl, bjh + bkh, bjh - bkh);
+}
+// rounds 4 + 2k and 5 + 2k.  ST: all seeds but the six that the two lane-0 constants reach are compile-time addresses
+template <bool ST>
+__device__ __forceinline__ void poseidon_double_partial_round(u64 (&s)[12], int k) {
+  double SL[6], DL[6], SH[6], DH[6];
+  SL[0] = poseidon_dbl_seed<ST, DBL_SL + 0>(k); DL[0] = poseidon_dbl_seed<ST, DBL_DL + 0>(k); SH[0] = poseidon_dbl_seed<ST, DBL_SH + 0>(k); DH[0] = poseidon_dbl_seed<ST, DBL_DH + 0>(k);
+  SL[1] = poseidon_dbl_seed<ST, DBL_SL + 1>(k); DL[1] = poseidon_dbl_seed<ST, DBL_DL + 1>(k); SH[1] = poseidon_dbl_seed<ST, DBL_SH + 1>(k); DH[1] = poseidon_dbl_seed<ST, DBL_DH + 1>(k);
+  SL[2] = poseidon_dbl_seed<ST, DBL_SL + 2>(k); DL[2] = poseidon_dbl_seed<ST, DBL_DL + 2>(k); SH[2] = poseidon_dbl_seed<ST, DBL_SH + 2>(k); DH[2] = poseidon_dbl_seed<ST, DBL_DH + 2>(k);
+  SL[3] = poseidon_dbl_seed<ST, DBL_SL + 3>(k); DL[3] = poseidon_dbl_seed<ST, DBL_DL + 3>(k); SH[3] = poseidon_dbl_seed<ST, DBL_SH + 3>(k); DH[3] = poseidon_dbl_seed<ST, DBL_DH + 3>(k);
+  SL[4] = poseidon_dbl_seed<ST, DBL_SL + 4>(k); DL[4] = poseidon_dbl_seed<ST, DBL_DL + 4>(k); SH[4] = poseidon_dbl_seed<ST, DBL_SH + 4>(k); DH[4] = poseidon_dbl_seed<ST, DBL_DH + 4>(k);
+  SL[5] = poseidon_dbl_seed<ST, DBL_SL + 5>(k); DL[5] = poseidon_dbl_seed<ST, DBL_DL + 5>(k); SH[5] = poseidon_dbl_seed<ST, DBL_SH + 5>(k); DH[5] = poseidon_dbl_seed<ST, DBL_DH + 5>(k);
+  const double stL = c_rcdbl.v[k][DBL_TL], stH = c_rcdbl.v[k][DBL_TH];
+  double tL = stL, tH = stH;
+  poseidon_dbl_pair<1>(s[1], s[7], tL, tH, SL, DL, SH, DH);
+  poseidon_dbl_pair<2>(s[2], s[8], tL, tH, SL, DL, SH, DH);
+  poseidon_dbl_pair<3>(s[3], s[9], tL, tH, SL, DL, SH, DH);
+  poseidon_dbl_pair<4>(s[4], s[10], tL, tH, SL, DL, SH, DH);
+  poseidon_dbl_pair<5>(s[5], s[11], tL, tH, SL, DL, SH, DH);
+  const u64 xr = poseidon_sbox(s[0]);  // first round's s-box
+  poseidon_dbl_pair<0>(xr, s[6], tL, tH, SL, DL, SH, DH);
+  // second round's s-box on lane 0 of the first layer; its result is only needed as the two parts of an unreduced product
+  double x1L, x1H;
+  poseidon_sbox_raw(poseidon_crt64_fold(tL, tH), x1L, x1H);
+  // w = 8 x_r + x' - t0 per part (t0 = t - seed, exact), the thirteenth input of the single layer's sums
+  const double wL = fma(__uint2double_rn((u32)xr), 8.0, stL - tL) + x1L;
+  const double wH = fma(__uint2double_rn((u32)(xr >> 32)), 8.0, stH - tH) + x1H;
+  poseidon_crt64_col<0, 0>(SL, DL, SH, DH, wL, wL, wH, wH);
+  poseidon_crt64_finish_d(s, x1L, x1H, SL, DL, SH, DH);  // + 8 x' on lane 0, recombination, folds
+}
+#define POSEIDON_HAVE_DOUBLE_ROUNDS 1
+#else
+#define POSEIDON_HAVE_DOUBLE_ROUNDS 0
+#endif
+
 // full round with the s-boxes and the layer in ONE basic block: the FP64/ALU work of a pair is independent of the
 // s-boxes still to come, so ptxas can interleave it with their wide multiplies (POSEIDON_SPLIT_ROUNDS)
 __device__ __forceinline__ void poseidon_full_round_crt64(u64 (&s)[12], int next_round) {
@@ -873,7 +1052,12 @@ __device__ __forceinline__ void poseidon_permute(u64 (&s)[12]) {
 #endif
       }
     } else {
-#if POSEIDON_MDS_F64 == 4 && POSEIDON_CRT_LEVEL2 && POSEIDON_EQUIV_RC
+#if POSEIDON_MDS_F64 == 4 && POSEIDON_HAVE_DOUBLE_ROUNDS
+      // the 22 partial rounds two at a time; the last pair hands the full constant vector on to the closing rounds
+#pragma unroll 1
+      for (int k = 0; k < 10; k++) poseidon_double_partial_round<true>(s, k);
+      poseidon_double_partial_round<false>(s, 10);
+#elif POSEIDON_MDS_F64 == 4 && POSEIDON_CRT_LEVEL2 && POSEIDON_EQUIV_RC
       // rounds 4..24 add a constant on lane 0 only (equivalent constants); round 25 hands the full vector on to the closing rounds
 #pragma unroll 1
       for (int r = 4; r < 25; r++) {
