@@ -167,6 +167,7 @@ def ncu_traffic(n):
         return None, "no committed ncu capture"
     t = json.load(open(files[-1]))
     per_proof = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["proofs"]
+    ncu_traffic.warp_inst_per_proof = t.get("warp_instructions", 0) / t["proofs"]
     return per_proof * n, "%s: dram read+write = %.1f MB for %d proofs = %.1f kB per proof (ncu --set full, %s); scaled to this launch" % (
         os.path.basename(files[-1]), (t["dram_bytes_read"] + t["dram_bytes_write"]) / 1e6, t["proofs"], per_proof / 1e3, t.get("report", "?"))
 
@@ -455,6 +456,14 @@ def main():
     algo_bytes = n * W * 8 + n * shape.num_queries * sum(lay.oracle_width[o] for o in range(4)) * 8 + 3 * n * lay.proof_words * 8
     hbm_achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic(n)
+    # issue-slot view of the same kernel: warp instructions per permutation from the committed capture x the measured rate,
+    # against 4 schedulers x SMs x the SM clock under load
+    inst_per_perm = getattr(ncu_traffic, "warp_inst_per_proof", 0) * 32 / (shape.num_queries * ppq)
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    issue_peak = 4.0 * sm_count * (clocks.get("sm_mhz") or 0) * 1e6
+    issue = {"warp_instructions_per_permutation": inst_per_perm, "issued_per_s": perms_per_s / 32 * inst_per_perm, "peak_per_s": issue_peak,
+             "frac": (perms_per_s / 32 * inst_per_perm / issue_peak) if issue_peak and inst_per_perm else None,
+             "source": "smsp__inst_executed.sum of the committed ncu capture / permutations of that launch; peak = 4 schedulers x %d SMs x SM clock under load" % sm_count}
 
     cpu = None
     os.sched_setaffinity(0, prev_affinity)  # the CPU baseline gets every host core again
@@ -478,7 +487,8 @@ def main():
                    "batch": "bundled %s fixture x %d, 3 of 4 copies tampered in one word" % (args.fixture, n),
                    "verdict_histogram": hist,
                    "host_placement": placement,
-                   "pipeline": "4 lanes (stream + workspace); chunks of 3 GiB (device-resident input) / 0.5 GiB (host input); K0/K4/K5 of the next chunks overlap K6 of the current one",
+                   "pipeline": "4 lanes (stream + workspace); device-resident input: 3 GiB chunks, K0/K4/K5 of the next chunks overlap K6 of the current one; host input: "
+                               "per-proof parts of the whole batch copied first (one strided copy), then 0.25 GiB chunks of query parts, transcripts ahead of the Merkle phases",
                    "multi_gpu": ("contiguous slices, one C-ABI call per step: p2v_verify_batch_sharded = verify + %s of the accept bitmap "
                                  "(libp2v's own communicator, NCCL %s)" % ("ncclAllGather" if args.gather == "nccl" else "peer-store gather (direct NVLink stores + flags)",
                                                                             ctx.nccl_info()[2])) if world > 1 else "single GPU"},
@@ -497,6 +507,10 @@ def main():
                      "perms_per_s": perms_per_s, "kernel_ms": fri_ms,
                      "peak_source": "IMAD.WIDE.U32 issue rate measured live on this GPU (p2v_int_pipe_peak mode 0: 32/clk/SM, "
                                     "i.e. half the 32-bit IMAD rate); algorithmic work = 6376 32x32->64 multiplies per permutation",
+                     "note": "frac may exceed 1: the unit is SURVEY 8(d)'s count for the textbook (fast-partial) permutation with every multiply on the "
+                             "integer pipe; this kernel runs the linear layers on the FP64 pipe (CRT-split dense MDS, two partial rounds as one layer) and "
+                             "needs 2192 wide multiplies per permutation, so the integer-pipe ceiling no longer binds — see `issue` for the resource that does",
+                     "issue": issue,
                      "imad32_peak": imad32_peak / 1e9, "frac_of_imad32_rate": achieved / imad32_peak,
                      "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                              "peak_source": hbm_src + " copy bandwidth (MEASURED_PEAKS.json)"}},

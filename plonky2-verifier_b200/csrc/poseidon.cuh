@@ -684,6 +684,8 @@ __device__ __forceinline__ void poseidon_l2_pair(u64 xj, u64 xk, double (&XL)[6]
 // 2^64 = 2^32 - 1 and 2^96 = -1 (mod p) is  (w0 - w2 - w3) + 2^32 (w1 + w2): the two parts the layer works on anyway, as exact
 // doubles in (-2^34, 2^32) and [0, 2^33).  4 conversions + 3 additions on the XU / FP64 pipes instead of the 10-instruction
 // carry chain + 2 conversions; the layer's seeds carry the offset that keeps its low sums non-negative.
+// (A reduction built from subtractions only — nothing but the wide multiplies on the FMA pipe, +3 instructions — measured 3.5%
+// slower in K6a: what counts is the instruction count, not that pipe.)
 __device__ __forceinline__ void poseidon_sbox_raw(u64 x, double &L, double &H) {
   u64 x2 = gl_mul(x, x);
   u64 x3 = gl_mul(x, x2);
@@ -801,8 +803,8 @@ __device__ __forceinline__ void poseidon_full_round_crt64_l2(u64 (&s)[12], int n
 //     M (x', (M v)_1..11) = M^2 v + col0(M) (x' - t0),      M^2 v = C^2 v + 8 x_r col0(C) + 8 t0 e_0
 //     =>  state after both rounds = C^2 v + col0(C) w + 8 x' e_0 (+ constants),     w = 8 x_r + x' - t0.
 // C^2 = circ(c * c) goes through the same CRT butterfly as C (its coefficients sum to 2^16: word sums < 2^49, exact), col0(C) w
-// is the contribution of a thirteenth input to the SINGLE layer's sums, and t0 costs 12 multiply-adds per part: 248 FP64
-// operations for two rounds instead of 360, one set of conversions and folds instead of two.  Every coefficient that reaches an
+// is the contribution of a thirteenth input to the SINGLE layer's sums, and t0 costs 12 multiply-adds per part: 234 FP64
+// operations for two rounds instead of 360 (with the second CRT level below), one set of conversions and folds instead of two.  Every coefficient that reaches an
 // output is non-negative (c*c >= 4586 > 41 * 41 + ...), so only the unreduced low part of x' needs the 2^42 lift of the fused
 // s-box.  Needs the equivalent round constants: the middle round adds a constant on lane 0 only.
 #ifndef POSEIDON_DOUBLE_ROUNDS
@@ -812,6 +814,7 @@ __device__ __forceinline__ void poseidon_full_round_crt64_l2(u64 (&s)[12], int n
 struct PoseidonSqCoef {
   int p2h[6], q2h[6];  // halved CRT coefficients of c * c (cyclic): (c2_d + c2_{d+6}) / 2, (c2_d - c2_{d+6}) / 2
   int m0[12];          // row 0 of M
+  int n3[3];           // (p2h_e - p2h_{e+3}) / 2
 };
 __host__ __device__ constexpr PoseidonSqCoef poseidon_make_sq_coef() {
   constexpr int c[12] = POSEIDON_MDS_ROW;
@@ -824,6 +827,7 @@ __host__ __device__ constexpr PoseidonSqCoef poseidon_make_sq_coef() {
     t.q2h[d] = (c2[d] - c2[d + 6]) / 2;
   }
   for (int j = 0; j < 12; j++) t.m0[j] = c[j] + (j == 0 ? 8 : 0);
+  for (int e = 0; e < 3; e++) t.n3[e] = (t.p2h[e] - t.p2h[e + 3]) / 2;
   return t;
 }
 constexpr bool poseidon_sq_coef_ok() {
@@ -834,6 +838,10 @@ constexpr bool poseidon_sq_coef_ok() {
     for (int j = 0; j < 12; j++) c2[k] += c[j] * c[(k - j + 12) % 12];
   for (int d = 0; d < 6; d++)
     if ((c2[d] + c2[d + 6]) % 2 || (c2[d] - c2[d + 6]) % 2) return false;
+  // second level: p2h_e + p2h_{e+3} = 2048 (5,6,5) and the differences are even
+  if (t.p2h[0] + t.p2h[3] != 2048 * 5 || t.p2h[1] + t.p2h[4] != 2048 * 6 || t.p2h[2] + t.p2h[5] != 2048 * 5) return false;
+  for (int e = 0; e < 3; e++)
+    if ((t.p2h[e] - t.p2h[e + 3]) % 2) return false;
   // every net coefficient of an input word in an output word is >= 0:  c2[(j-i)] - C[i][0] m0[j] (+ 8 C[i][0] for j = 0)
   for (int i = 0; i < 12; i++)
     for (int j = 0; j < 12; j++)
@@ -842,12 +850,18 @@ constexpr bool poseidon_sq_coef_ok() {
 }
 static_assert(poseidon_sq_coef_ok(), "double partial rounds: coefficient conditions");
 
-// seeds of double round k (rounds 4 + 2k and 5 + 2k): [0..5] S low, [6..11] D low, [12..17] S high, [18..23] D high for the
-// constants of round 6 + 2k, then the two parts of the seed of t0 (lane-0 constant of round 5 + 2k)
+// Second CRT level on the cyclic half of C^2, as for the single layer: S_i = sum_j p2h_{(j-i) mod 6} X_j with A_k = X_k + X_{k+3},
+// B_k = X_k - X_{k+3}:  p2h_e + p2h_{e+3} = 2048 (5,6,5),  p2h_e - p2h_{e+3} = (264,-480,-96), halved again:
+//     S_i = 1024 E_i + SD_i,  S_{i+3} = 1024 E_i - SD_i,   E_i = 5 (A_0 + A_1 + A_2) + A_{(i+1) mod 3},   SD_i = sum_k n_{(k-i) mod 6} B_k,
+//     n = (132,-240,-48,-132,240,48)                                        29 FP64 operations per part instead of 36.
+// Seeds of double round k (rounds 4 + 2k and 5 + 2k), for the constants of round 6 + 2k: [0..5] D low, [6..11] D high, [12..14] e low,
+// [15..17] g low, [18..20] e high, [21..23] g high with 1024 e_i + g_i = 2^52 + sigma_i, 1024 e_i - g_i = 2^52 + sigma_{i+3} (sigma = the S seed
+// of the one-level form; e_i has ten fractional bits next to 2^42: exact), then the two parts of the seed of t0 (lane-0 constant of
+// round 5 + 2k).
 struct alignas(16) PoseidonRcDbl {
   double v[11][26];
 };
-enum { DBL_SL = 0, DBL_DL = 6, DBL_SH = 12, DBL_DH = 18, DBL_TL = 24, DBL_TH = 25 };
+enum { DBL_DL = 0, DBL_DH = 6, DBL_EL = 12, DBL_GL = 15, DBL_EH = 18, DBL_GH = 21, DBL_TL = 24, DBL_TH = 25 };
 __host__ __device__ constexpr PoseidonRcDbl poseidon_make_rc_dbl() {
   constexpr PoseidonEquivRc rce = poseidon_make_equiv_rc(true);
   constexpr u64 kadj = ((u64)P2V_F64_K << 33) - (u64)P2V_F64_K;
@@ -855,22 +869,38 @@ __host__ __device__ constexpr PoseidonRcDbl poseidon_make_rc_dbl() {
   PoseidonRcDbl t{};
   for (int k = 0; k < 11; k++) {
     const int r1 = 5 + 2 * k, r2 = 6 + 2 * k;
+    u64 alo[6] = {}, ahi[6] = {}, blo[6] = {}, bhi[6] = {};
     for (int i = 0; i < 6; i++) {
       u64 a = poseidon_addmod_c(rce.v[r2][i], cadj), b = poseidon_addmod_c(rce.v[r2][i + 6], cadj);
-      u64 alo = a & 0xFFFFFFFFULL, ahi = a >> 32, blo = b & 0xFFFFFFFFULL, bhi = b >> 32;
+      alo[i] = a & 0xFFFFFFFFULL; ahi[i] = a >> 32; blo[i] = b & 0xFFFFFFFFULL; bhi[i] = b >> 32;
       // the unreduced low part of x' is in (-2^34, 2^32) and reaches every output with a coefficient <= 49: lift the low parts by
       // 2^42, take 2^10 off the high parts (same value); a high part below 2^10 is first moved up by p
-      if (ahi < 1024) { alo += 1; ahi += 0xFFFFFFFFULL; }
-      if (bhi < 1024) { blo += 1; bhi += 0xFFFFFFFFULL; }
-      alo += 1ULL << 42; blo += 1ULL << 42; ahi -= 1024; bhi -= 1024;
-      bool flo = ((alo ^ blo) & 1) != 0, fhi = ((ahi ^ bhi) & 1) != 0;
-      if (flo && fhi) { blo += 1; bhi += 0xFFFFFFFFULL; }
-      else if (flo) { blo += 1 + (1ULL << 32); bhi += 0xFFFFFFFEULL; }
-      else if (fhi) { blo += 1ULL << 32; bhi -= 1; }
-      t.v[k][DBL_SL + i] = P2V_TWO52 + (double)((alo + blo) / 2);
-      t.v[k][DBL_DL + i] = (double)(((long long)alo - (long long)blo) / 2);
-      t.v[k][DBL_SH + i] = P2V_TWO52 + (double)((ahi + bhi) / 2);
-      t.v[k][DBL_DH + i] = (double)(((long long)ahi - (long long)bhi) / 2);
+      if (ahi[i] < 1024) { alo[i] += 1; ahi[i] += 0xFFFFFFFFULL; }
+      if (bhi[i] < 1024) { blo[i] += 1; bhi[i] += 0xFFFFFFFFULL; }
+      alo[i] += 1ULL << 42; blo[i] += 1ULL << 42; ahi[i] -= 1024; bhi[i] -= 1024;
+      bool flo = ((alo[i] ^ blo[i]) & 1) != 0, fhi = ((ahi[i] ^ bhi[i]) & 1) != 0;
+      if (flo && fhi) { blo[i] += 1; bhi[i] += 0xFFFFFFFFULL; }
+      else if (flo) { blo[i] += 1 + (1ULL << 32); bhi[i] += 0xFFFFFFFEULL; }
+      else if (fhi) { blo[i] += 1ULL << 32; bhi[i] -= 1; }
+    }
+    for (int i = 0; i < 3; i++) {  // sigma_i + sigma_{i+3} even in both parts, by moving a_i (lane 0 is the only one that varies)
+      bool olo = (((alo[i] + blo[i]) / 2 + (alo[i + 3] + blo[i + 3]) / 2) & 1) != 0;
+      bool ohi = (((ahi[i] + bhi[i]) / 2 + (ahi[i + 3] + bhi[i + 3]) / 2) & 1) != 0;
+      if (olo && ohi) { alo[i] += 2; ahi[i] += (1ULL << 33) - 2; }
+      else if (olo) { alo[i] += 2 + (1ULL << 33); ahi[i] += (1ULL << 33) - 4; }
+      else if (ohi) { alo[i] += 4 + (1ULL << 33); ahi[i] += (1ULL << 34) - 6; }
+    }
+    for (int i = 0; i < 6; i++) {
+      t.v[k][DBL_DL + i] = (double)(((long long)alo[i] - (long long)blo[i]) / 2);
+      t.v[k][DBL_DH + i] = (double)(((long long)ahi[i] - (long long)bhi[i]) / 2);
+    }
+    for (int i = 0; i < 3; i++) {
+      long long sl0 = (long long)((alo[i] + blo[i]) / 2), sl3 = (long long)((alo[i + 3] + blo[i + 3]) / 2);
+      long long sh0 = (long long)((ahi[i] + bhi[i]) / 2), sh3 = (long long)((ahi[i + 3] + bhi[i + 3]) / 2);
+      t.v[k][DBL_EL + i] = P2V_TWO52 / 1024.0 + (double)((sl0 + sl3) / 2) / 1024.0;
+      t.v[k][DBL_GL + i] = (double)((sl0 - sl3) / 2);
+      t.v[k][DBL_EH + i] = P2V_TWO52 / 1024.0 + (double)((sh0 + sh3) / 2) / 1024.0;
+      t.v[k][DBL_GH + i] = (double)((sh0 - sh3) / 2);
     }
     u64 a = poseidon_addmod_c(rce.v[r1][0], cadj);
     t.v[k][DBL_TL] = P2V_TWO52 + (double)(a & 0xFFFFFFFFULL);
@@ -878,7 +908,7 @@ __host__ __device__ constexpr PoseidonRcDbl poseidon_make_rc_dbl() {
   }
   return t;
 }
-__host__ __device__ constexpr bool poseidon_dbl_seed_varies(int k) { return k == DBL_SL || k == DBL_DL || k == DBL_SH || k == DBL_DH || k >= DBL_TL; }
+__host__ __device__ constexpr bool poseidon_dbl_seed_varies(int k) { return k == DBL_DL || k == DBL_DH || k == DBL_EL || k == DBL_GL || k == DBL_EH || k == DBL_GH || k >= DBL_TL; }
 constexpr bool poseidon_dbl_static_ok() {
   constexpr PoseidonRcDbl t = poseidon_make_rc_dbl();
   constexpr PoseidonEquivRc rce = poseidon_make_equiv_rc(true);
@@ -902,8 +932,7 @@ __host__ __device__ constexpr PoseidonRcDblStatic poseidon_make_rc_dbl_static() 
   return r;
 }
 
-// the round-independent seeds as compile-time values: ten of the D seeds are zero (a multiply instead of a multiply-add), the ten
-// S seeds are one value per part
+// the round-independent seeds as compile-time values (ten of the D seeds and the four static g are zero)
 constexpr PoseidonRcDblStatic k_rcdbls = poseidon_make_rc_dbl_static();
 template <bool ST, int K>
 __device__ __forceinline__ double poseidon_dbl_seed(int k) {
@@ -913,23 +942,19 @@ __device__ __forceinline__ double poseidon_dbl_seed(int k) {
   }
   return c_rcdbl.v[k][K];
 }
-// contribution of input pair J to the C^2 sums of rows I..5
+// contribution of input pair J to the negacyclic half (D) of the C^2 sums, rows I..5
 template <int J, int I>
-__device__ __forceinline__ void poseidon_dbl_col(double (&SL)[6], double (&DL)[6], double (&SH)[6], double (&DH)[6], double xpL, double xmL, double xpH,
-                                                 double xmH) {
+__device__ __forceinline__ void poseidon_dbl_dcol(double (&DL)[6], double (&DH)[6], double xmL, double xmH) {
   constexpr PoseidonSqCoef cf = poseidon_make_sq_coef();
   constexpr int d = (J - I + 12) % 12;
-  constexpr double pc = (double)cf.p2h[d % 6];
   constexpr double qc = (double)(d < 6 ? cf.q2h[d] : -cf.q2h[d - 6]);
-  SL[I] = fma(xpL, pc, SL[I]);
   DL[I] = fma(xmL, qc, DL[I]);
-  SH[I] = fma(xpH, pc, SH[I]);
   DH[I] = fma(xmH, qc, DH[I]);
-  if constexpr (I + 1 < 6) poseidon_dbl_col<J, I + 1>(SL, DL, SH, DH, xpL, xmL, xpH, xmH);
+  if constexpr (I + 1 < 6) poseidon_dbl_dcol<J, I + 1>(DL, DH, xmL, xmH);
 }
-// pair (v_J, v_{J+6}): conversions, its share of t0, butterfly, C^2 sums
+// pair (v_J, v_{J+6}): conversions, its share of t0, butterfly, D sums; X+ is kept for the second level
 template <int J>
-__device__ __forceinline__ void poseidon_dbl_pair(u64 xj, u64 xk, double &tL, double &tH, double (&SL)[6], double (&DL)[6], double (&SH)[6],
+__device__ __forceinline__ void poseidon_dbl_pair(u64 xj, u64 xk, double &tL, double &tH, double (&XL)[6], double (&XH)[6], double (&DL)[6],
                                                   double (&DH)[6]) {
   constexpr PoseidonSqCoef cf = poseidon_make_sq_coef();
   double bjl = __uint2double_rn((u32)xj), bjh = __uint2double_rn((u32)(xj >> 32));
@@ -938,30 +963,59 @@ __device__ __forceinline__ void poseidon_dbl_pair(u64 xj, u64 xk, double &tL, do
   tH = fma(bjh, (double)cf.m0[J], tH);
   tL = fma(bkl, (double)cf.m0[J + 6], tL);
   tH = fma(bkh, (double)cf.m0[J + 6], tH);
-  poseidon_dbl_col<J, 0>(SL, DL, SH, DH, bjl + bkl, bjl - bkl, bjh + bkh, bjh - bkh);
+  XL[J] = bjl + bkl;
+  XH[J] = bjh + bkh;
+  poseidon_dbl_dcol<J, 0>(DL, DH, bjl - bkl, bjh - bkh);
+}
+// cyclic half of one part from the six X+ (second CRT level)
+__device__ __forceinline__ void poseidon_dbl_s(const double (&X)[6], const double (&e)[3], const double (&g)[3], double (&S)[6]) {
+  constexpr PoseidonSqCoef cf = poseidon_make_sq_coef();
+  constexpr double n0 = (double)cf.n3[0], n1 = (double)cf.n3[1], n2 = (double)cf.n3[2];
+  double A0 = X[0] + X[3], A1 = X[1] + X[4], A2 = X[2] + X[5];
+  double B0 = X[0] - X[3], B1 = X[1] - X[4], B2 = X[2] - X[5];
+  double sum = (A0 + A1) + A2;
+  double E0 = fma(sum, 5.0, A1 + e[0]), E1 = fma(sum, 5.0, A2 + e[1]), E2 = fma(sum, 5.0, A0 + e[2]);
+  // SD_i = sum_k n_{(k-i) mod 6} B_k,  n_{e+3} = -n_e
+  double SD0 = fma(B2, n2, fma(B1, n1, fma(B0, n0, g[0])));
+  double SD1 = fma(B0, -n2, fma(B2, n1, fma(B1, n0, g[1])));
+  double SD2 = fma(B1, -n2, fma(B0, -n1, fma(B2, n0, g[2])));
+  S[0] = fma(E0, 1024.0, SD0); S[3] = fma(E0, 1024.0, -SD0);
+  S[1] = fma(E1, 1024.0, SD1); S[4] = fma(E1, 1024.0, -SD1);
+  S[2] = fma(E2, 1024.0, SD2); S[5] = fma(E2, 1024.0, -SD2);
 }
 // rounds 4 + 2k and 5 + 2k.  ST: all seeds but the six that the two lane-0 constants reach are compile-time addresses
 template <bool ST>
 __device__ __forceinline__ void poseidon_double_partial_round(u64 (&s)[12], int k) {
-  double SL[6], DL[6], SH[6], DH[6];
-  SL[0] = poseidon_dbl_seed<ST, DBL_SL + 0>(k); DL[0] = poseidon_dbl_seed<ST, DBL_DL + 0>(k); SH[0] = poseidon_dbl_seed<ST, DBL_SH + 0>(k); DH[0] = poseidon_dbl_seed<ST, DBL_DH + 0>(k);
-  SL[1] = poseidon_dbl_seed<ST, DBL_SL + 1>(k); DL[1] = poseidon_dbl_seed<ST, DBL_DL + 1>(k); SH[1] = poseidon_dbl_seed<ST, DBL_SH + 1>(k); DH[1] = poseidon_dbl_seed<ST, DBL_DH + 1>(k);
-  SL[2] = poseidon_dbl_seed<ST, DBL_SL + 2>(k); DL[2] = poseidon_dbl_seed<ST, DBL_DL + 2>(k); SH[2] = poseidon_dbl_seed<ST, DBL_SH + 2>(k); DH[2] = poseidon_dbl_seed<ST, DBL_DH + 2>(k);
-  SL[3] = poseidon_dbl_seed<ST, DBL_SL + 3>(k); DL[3] = poseidon_dbl_seed<ST, DBL_DL + 3>(k); SH[3] = poseidon_dbl_seed<ST, DBL_SH + 3>(k); DH[3] = poseidon_dbl_seed<ST, DBL_DH + 3>(k);
-  SL[4] = poseidon_dbl_seed<ST, DBL_SL + 4>(k); DL[4] = poseidon_dbl_seed<ST, DBL_DL + 4>(k); SH[4] = poseidon_dbl_seed<ST, DBL_SH + 4>(k); DH[4] = poseidon_dbl_seed<ST, DBL_DH + 4>(k);
-  SL[5] = poseidon_dbl_seed<ST, DBL_SL + 5>(k); DL[5] = poseidon_dbl_seed<ST, DBL_DL + 5>(k); SH[5] = poseidon_dbl_seed<ST, DBL_SH + 5>(k); DH[5] = poseidon_dbl_seed<ST, DBL_DH + 5>(k);
+  double XL[6], XH[6], DL[6], DH[6];
+  DL[0] = poseidon_dbl_seed<ST, DBL_DL + 0>(k); DH[0] = poseidon_dbl_seed<ST, DBL_DH + 0>(k);
+  DL[1] = poseidon_dbl_seed<ST, DBL_DL + 1>(k); DH[1] = poseidon_dbl_seed<ST, DBL_DH + 1>(k);
+  DL[2] = poseidon_dbl_seed<ST, DBL_DL + 2>(k); DH[2] = poseidon_dbl_seed<ST, DBL_DH + 2>(k);
+  DL[3] = poseidon_dbl_seed<ST, DBL_DL + 3>(k); DH[3] = poseidon_dbl_seed<ST, DBL_DH + 3>(k);
+  DL[4] = poseidon_dbl_seed<ST, DBL_DL + 4>(k); DH[4] = poseidon_dbl_seed<ST, DBL_DH + 4>(k);
+  DL[5] = poseidon_dbl_seed<ST, DBL_DL + 5>(k); DH[5] = poseidon_dbl_seed<ST, DBL_DH + 5>(k);
   const double stL = c_rcdbl.v[k][DBL_TL], stH = c_rcdbl.v[k][DBL_TH];
   double tL = stL, tH = stH;
-  poseidon_dbl_pair<1>(s[1], s[7], tL, tH, SL, DL, SH, DH);
-  poseidon_dbl_pair<2>(s[2], s[8], tL, tH, SL, DL, SH, DH);
-  poseidon_dbl_pair<3>(s[3], s[9], tL, tH, SL, DL, SH, DH);
-  poseidon_dbl_pair<4>(s[4], s[10], tL, tH, SL, DL, SH, DH);
-  poseidon_dbl_pair<5>(s[5], s[11], tL, tH, SL, DL, SH, DH);
+  poseidon_dbl_pair<1>(s[1], s[7], tL, tH, XL, XH, DL, DH);
+  poseidon_dbl_pair<2>(s[2], s[8], tL, tH, XL, XH, DL, DH);
+  poseidon_dbl_pair<3>(s[3], s[9], tL, tH, XL, XH, DL, DH);
+  poseidon_dbl_pair<4>(s[4], s[10], tL, tH, XL, XH, DL, DH);
+  poseidon_dbl_pair<5>(s[5], s[11], tL, tH, XL, XH, DL, DH);
   const u64 xr = poseidon_sbox(s[0]);  // first round's s-box
-  poseidon_dbl_pair<0>(xr, s[6], tL, tH, SL, DL, SH, DH);
+  poseidon_dbl_pair<0>(xr, s[6], tL, tH, XL, XH, DL, DH);
   // second round's s-box on lane 0 of the first layer; its result is only needed as the two parts of an unreduced product
   double x1L, x1H;
   poseidon_sbox_raw(poseidon_crt64_fold(tL, tH), x1L, x1H);
+  // cyclic half of C^2 v (independent of the second s-box)
+  double SL[6], SH[6];
+  {
+    double el[3], gl[3], eh[3], gh[3];
+    el[0] = poseidon_dbl_seed<ST, DBL_EL + 0>(k); el[1] = poseidon_dbl_seed<ST, DBL_EL + 1>(k); el[2] = poseidon_dbl_seed<ST, DBL_EL + 2>(k);
+    gl[0] = poseidon_dbl_seed<ST, DBL_GL + 0>(k); gl[1] = poseidon_dbl_seed<ST, DBL_GL + 1>(k); gl[2] = poseidon_dbl_seed<ST, DBL_GL + 2>(k);
+    eh[0] = poseidon_dbl_seed<ST, DBL_EH + 0>(k); eh[1] = poseidon_dbl_seed<ST, DBL_EH + 1>(k); eh[2] = poseidon_dbl_seed<ST, DBL_EH + 2>(k);
+    gh[0] = poseidon_dbl_seed<ST, DBL_GH + 0>(k); gh[1] = poseidon_dbl_seed<ST, DBL_GH + 1>(k); gh[2] = poseidon_dbl_seed<ST, DBL_GH + 2>(k);
+    poseidon_dbl_s(XL, el, gl, SL);
+    poseidon_dbl_s(XH, eh, gh, SH);
+  }
   // w = 8 x_r + x' - t0 per part (t0 = t - seed, exact), the thirteenth input of the single layer's sums
   const double wL = fma(__uint2double_rn((u32)xr), 8.0, stL - tL) + x1L;
   const double wH = fma(__uint2double_rn((u32)(xr >> 32)), 8.0, stH - tH) + x1H;
