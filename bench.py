@@ -509,7 +509,7 @@ def main():
                                     "i.e. half the 32-bit IMAD rate); algorithmic work = 6376 32x32->64 multiplies per permutation",
                      "note": "frac may exceed 1: the unit is SURVEY 8(d)'s count for the textbook (fast-partial) permutation with every multiply on the "
                              "integer pipe; this kernel runs the linear layers on the FP64 pipe (CRT-split dense MDS, two partial rounds as one layer) and "
-                             "needs 2192 wide multiplies per permutation, so the integer-pipe ceiling no longer binds — see `issue` for the resource that does",
+                             "issues ~2250 half-rate multiplies (IMAD.WIDE + IMAD.HI, the s-boxes) per permutation, so the integer-pipe ceiling no longer binds — see `issue` for the resource that does",
                      "issue": issue,
                      "imad32_peak": imad32_peak / 1e9, "frac_of_imad32_rate": achieved / imad32_peak,
                      "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
