@@ -16,6 +16,8 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 OUT = os.path.join(HERE, "libp2v.so")
 OBJ = os.path.join(HERE, "build")
+APPS = os.path.join(HERE, "apps")
+TESTMAIN = os.path.join(HERE, "p2v_testmain")  # the reference's driver (src/testmain.hs) above the C ABI
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -51,6 +53,9 @@ def _deps_hash():
             if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 with open(os.path.join(dirpath, f), "rb") as fh:
                     h.update(f.encode() + fh.read())
+    for f in sorted(os.listdir(APPS)):
+        with open(os.path.join(APPS, f), "rb") as fh:
+            h.update(f.encode() + fh.read())
     with open(os.path.join(ROOT, "include", "p2v.h"), "rb") as fh:
         h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS + CXX_FLAGS).encode())
@@ -61,7 +66,7 @@ def build(force=False, verbose=False):
     """Compile every translation unit under csrc/ and link libp2v.so.  Idempotent (content hash)."""
     stamp = os.path.join(OBJ, "stamp")
     want = _deps_hash()
-    if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == want:
+    if not force and os.path.exists(OUT) and os.path.exists(TESTMAIN) and os.path.exists(stamp) and open(stamp).read() == want:
         return OUT
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
@@ -89,6 +94,11 @@ def build(force=False, verbose=False):
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    # host programs above the C ABI: plain g++, include/p2v.h only, libp2v.so found next to the binary
+    app = ["g++"] + CXX_FLAGS + [os.path.join(APPS, "testmain.cpp"), "-o", TESTMAIN, "-L", HERE, "-lp2v", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(app, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("p2v_testmain failed to build:\n" + r.stdout + r.stderr)
     with open(stamp, "w") as fh:
         fh.write(want)
     return OUT

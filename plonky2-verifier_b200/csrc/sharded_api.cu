@@ -328,9 +328,22 @@ int p2v_verify_batch_sharded(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t 
   uint32_t *mine = full.as<uint32_t>() + (size_t)rank * words_per_rank;
   // padding words of a short (or empty) last slice are zero; K7 writes ceil(n_local/32) words
   P2V_CUDA(ctx, cudaMemsetAsync(mine, 0, words_per_rank * 4, ctx->stream));
+  // The call is a COLLECTIVE: a rank whose slice cannot be verified (bad pointer, out of memory, shape mismatch ...) must
+  // still take part in the exchange, or every other rank would wait for it forever.  It contributes an all-zero slice
+  // (nothing accepted), completes the gather, and only then reports its error.
+  int rc_local = P2V_OK;
+  std::string err_local;
   if (n_local) {
-    if ((rc = p2v_verify_batch(ctx, c, blobs_local, n_local, mine, status_local))) return rc;
+    rc_local = p2v_verify_batch(ctx, c, blobs_local, n_local, mine, status_local);
+    if (rc_local != P2V_OK) {
+      err_local = ctx->err;
+      if (world == 1) return rc_local;
+      cudaGetLastError();
+      if (cudaMemsetAsync(mine, 0, words_per_rank * 4, ctx->stream) != cudaSuccess) return rc_local;  // sticky CUDA error: nothing more can run
+    }
   }
+#define P2V_SHARDED_DONE() \
+  do { if (rc_local != P2V_OK) return p2v_fail(ctx, rc_local, err_local + " (this rank contributed an all-zero slice to the gather)"); return P2V_OK; } while (0)
   p2v_peer_state *ps = (p2v_peer_state *)ctx->peer;
   if (world > 1 && ps && ps->world == world && ps->rank == rank && words_full <= P2V_PEER_MAX_WORDS) {
     // direct stores into every peer's buffer + flags (no NCCL kernel on the path)
@@ -346,9 +359,8 @@ int p2v_verify_batch_sharded(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t 
       P2V_CUDA(ctx, cudaMemcpyAsync(&timed_out, &ps->local->timed_out, 4, cudaMemcpyDeviceToHost, ctx->stream));
       P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       if (timed_out) return p2v_fail(ctx, P2V_E_CUDA, "p2v_verify_batch_sharded: a peer did not publish its slice in time");
-      return P2V_OK;
     }
-    return P2V_OK;
+    P2V_SHARDED_DONE();
   }
   if (world > 1) {
     // in place: rank r's words already sit at recvbuff + r * count
@@ -356,7 +368,8 @@ int p2v_verify_batch_sharded(p2v_ctx *ctx, const p2v_circuit *c, const uint64_t 
   }
   if ((rc = full.finish())) return rc;
   if (full.host) P2V_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return P2V_OK;
+  P2V_SHARDED_DONE();
+#undef P2V_SHARDED_DONE
 }
 
 }  // extern "C"

@@ -58,8 +58,39 @@ def main():
                 assert not allbits[r * per + (b - a):(r + 1) * per].any(), "padding bits set"
                 assert np.array_equal(allbits[r * per: r * per + (b - a)], want[a:b] == 0), "rank %d's slice is not at words [%d, %d)" % (r, r * per // 32, (r + 1) * per // 32)
         cir.close()
+    # ---- the call is a collective: a rank whose slice cannot be verified still takes part in the gather (all-zero slice),
+    # the other ranks neither hang nor see accepted proofs there, and only the failing rank reports an error ----
+    def failing_rank_case(tag):
+        ctx_other = p2v.Context(local)
+        shape, lay, vkey, blob = fixtures.load("small6")
+        cir, foreign = p2v.Circuit(ctx, shape, vkey), p2v.Circuit(ctx_other, shape, vkey)  # `foreign` belongs to another context
+        n_total, bad = 48 * world + 5, 0
+        blobs, _, _ = fixtures.tampered_batch(blob, lay, shape, n_total, seed=5)
+        want = orc.verify_batch(shape, vkey, blobs, threads=8, fast=True)["status"]
+        start, stop = p2v.shard_bounds(n_total, rank, world)
+        raw = np.zeros(p2v.shard_slice_len(n_total, world) // 32 * world, dtype=np.uint32)
+        st = np.empty(max(stop - start, 1), dtype=np.uint32)
+        local_blobs = np.ascontiguousarray(blobs[start:stop])
+        rc = p2v.lib().p2v_verify_batch_sharded(ctx._h, (foreign if rank == bad else cir)._h, p2v._ptr(local_blobs), n_total, rank, world,
+                                                p2v._ptr(raw), p2v._ptr(st))
+        if rank == bad:
+            assert rc == -1 and b"all-zero slice" in p2v.lib().p2v_last_error(ctx._h), (tag, rc)
+        else:
+            assert rc == 0, (tag, rank, rc)
+        expect = want == 0
+        a, b = p2v.shard_bounds(n_total, bad, world)
+        assert expect[a:b].any(), "the failing rank's slice must hold proofs that would have been accepted"
+        expect[a:b] = False
+        assert np.array_equal(p2v.unpack_bits(raw, n_total), expect), (tag, rank, "gather after a local failure")
+        # and the communicator is still usable afterwards
+        acc, _ = cir.verifyProofSharded(local_blobs, n_total, rank, world)
+        assert np.array_equal(acc, want == 0), (tag, rank, "call after a local failure")
+        cir.close(); foreign.close(); ctx_other.close()
+
+    failing_rank_case("nccl")
     # ---- the gather without NCCL: direct stores into the peers' buffers + flags (p2v_peer_enable) ----
     ctx.peer_enable()
+    failing_rank_case("peer")
     shape, lay, vkey, blob = fixtures.load("small6")
     cir = p2v.Circuit(ctx, shape, vkey)
     for rep, n_total in enumerate((100, 33, 64, 100, 7, 256, 100)):  # several epochs back to back: both halves of the buffers
