@@ -17,7 +17,11 @@ ROOT = os.path.dirname(HERE)
 OUT = os.path.join(HERE, "libp2v.so")
 OBJ = os.path.join(HERE, "build")
 APPS = os.path.join(HERE, "apps")
-TESTMAIN = os.path.join(HERE, "p2v_testmain")  # the reference's driver (src/testmain.hs) above the C ABI
+# host programs above the C ABI (apps/<name>.cpp -> p2v_<name>): testmain = the reference's driver (src/testmain.hs),
+# shard_demo = BASELINE config 5 from a host without Python or torch (one process per GPU, NCCL bootstrapped through the C ABI)
+APP_NAMES = ["testmain", "shard_demo"]
+APP_BINS = [os.path.join(HERE, "p2v_" + a) for a in APP_NAMES]
+TESTMAIN = APP_BINS[0]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -66,7 +70,7 @@ def build(force=False, verbose=False):
     """Compile every translation unit under csrc/ and link libp2v.so.  Idempotent (content hash)."""
     stamp = os.path.join(OBJ, "stamp")
     want = _deps_hash()
-    if not force and os.path.exists(OUT) and os.path.exists(TESTMAIN) and os.path.exists(stamp) and open(stamp).read() == want:
+    if not force and os.path.exists(OUT) and all(os.path.exists(b) for b in APP_BINS) and os.path.exists(stamp) and open(stamp).read() == want:
         return OUT
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
@@ -95,10 +99,11 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     # host programs above the C ABI: plain g++, include/p2v.h only, libp2v.so found next to the binary
-    app = ["g++"] + CXX_FLAGS + [os.path.join(APPS, "testmain.cpp"), "-o", TESTMAIN, "-L", HERE, "-lp2v", "-Wl,-rpath,$ORIGIN"]
-    r = subprocess.run(app, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("p2v_testmain failed to build:\n" + r.stdout + r.stderr)
+    for name, out in zip(APP_NAMES, APP_BINS):
+        app = ["g++"] + CXX_FLAGS + [os.path.join(APPS, name + ".cpp"), "-o", out, "-L", HERE, "-lp2v", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(app, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("p2v_%s failed to build:\n" % name + r.stdout + r.stderr)
     with open(stamp, "w") as fh:
         fh.write(want)
     return OUT
