@@ -285,6 +285,84 @@ static Preset makePreset(const std::string &name) {
     for (u64 i = 0; i < 19; i++) t0.push_back({i, (i * i + 3) & 0xffff});
     for (u64 i = 0; i < 8; i++) t1.push_back({100 + i, 7 * i + 1});
     p.luts = {t0, t1};
+  } else if (name.rfind("rand", 0) == 0 || name.rfind("rreal", 0) == 0) {
+    // Random VALID shapes for the property tests (tests/test_random_shapes.py, tests/test_gpu_random_shapes.py): every
+    // parameter of CommonCircuitData that the verifier's layout, transcript, gate programs or FRI schedule depend on is
+    // drawn from the preset's number.  rand<K>: all-Noop rows (any gate set and any quotient_degree_factor are valid: the
+    // filters vanish identically); rreal<K>: the real circuit of real5 (active gates, copy constraints, real quotient,
+    // rate_bits 3 = log2 quotient_degree_factor) under random FRI parameters.
+    const bool real = name[1] == 'r';
+    const u64 k = strtoull(name.c_str() + (real ? 5 : 4), nullptr, 10);
+    SplitMix g(0xC0FFEEULL ^ (k * 0x9E3779B97F4A7C15ULL) ^ (real ? 0x5EA1ULL : 0));
+    auto pick = [&](int lo, int hi) { return lo + (int)(g.next() % (u64)(hi - lo + 1)); };
+    p.real = real;
+    p.degree_bits = real ? pick(5, 8) : pick(3, 9);
+    p.rate_bits = real ? 3 : pick(1, 4);
+    p.qdf = real ? 8 : 1 << pick(1, 3);
+    p.num_challenges = real ? 2 : pick(1, 3);
+    p.pow_bits = pick(0, 10);
+    p.num_queries = pick(1, 9);
+    // reduction strategy: ConstantArityBits (a, f) with f chosen so that the folding ends exactly at 2^f coefficients, or Fixed
+    int total = 0;
+    if (pick(0, 2) == 0) {
+      p.fixed_strategy = true;
+      for (int left = p.degree_bits; left > 0 && (int)p.fixed_arities.size() < 4 && pick(0, 3) != 0;) {
+        int a = pick(1, std::min(5, left));
+        p.fixed_arities.push_back(a);
+        left -= a;
+        total += a;
+      }
+    } else {
+      p.arity_bits = pick(1, 4);
+      int steps = pick(0, p.degree_bits / p.arity_bits);
+      total = steps * p.arity_bits;
+      p.final_poly_bits = p.degree_bits - total;
+    }
+    p.cap_height = pick(0, std::min(4, p.degree_bits + p.rate_bits - total));  // every commit-phase tree is at least as high as its cap
+    if (real) {
+      p.num_wires = 135; p.num_routed = 80; p.num_public_inputs = pick(0, 9);
+      p.gates = {gNoop(), gConst(2), gPI(), gBaseSum(63, 2), gRedExt(32), gRed(43), gArithExt(10), gArith(20), gMulExt(13),
+                 gExp(66), gRA(4, 4, 2), gCoset(4, 6), gPoseidon(), gPoseidonMds()};
+      assignGroups(p, {6, 4, 2, 2});
+    } else {
+      const bool wide = pick(0, 1) == 1;
+      p.num_wires = wide ? 135 : pick(8, 60);
+      p.num_routed = wide ? 80 : pick(2, p.num_wires);
+      p.num_public_inputs = pick(0, 9);
+      const int W = p.num_wires;
+      std::vector<GateSpec> pool;
+      pool.push_back(gConst(pick(1, 2)));
+      if (W >= 4) pool.push_back(gPI());
+      pool.push_back(gArith(pick(1, std::min(20, W / 4))));
+      pool.push_back(gArithExt(pick(1, std::min(10, W / 8))));
+      pool.push_back(gMulExt(pick(1, std::min(13, W / 6))));
+      pool.push_back(gBaseSum(pick(1, std::min(63, W - 1)), pick(2, 4)));
+      if (W >= 9) pool.push_back(gRed(pick(1, std::min(43, (W - 6) / 3))));
+      if (W >= 10) pool.push_back(gRedExt(pick(1, std::min(32, (W - 6) / 4))));
+      if (W >= 4) pool.push_back(gExp(pick(1, std::min(66, (W - 2) / 2))));
+      if (wide) {
+        int bits = pick(1, 4);
+        pool.push_back(gRA(bits, pick(1, 4), pick(0, 2)));
+        int cb = pick(2, 4);
+        pool.push_back(gCoset(cb, pick(2, 7)));
+        pool.push_back(gPoseidon());
+        pool.push_back(gPoseidonMds());
+      }
+      // a random subset in random order, the NoopGate somewhere among them
+      std::vector<GateSpec> chosen;
+      for (auto &gs : pool)
+        if (pick(0, 2) != 0) chosen.push_back(gs);
+      chosen.insert(chosen.begin() + pick(0, (int)chosen.size()), gNoop());
+      for (size_t i = chosen.size(); i > 1; i--) std::swap(chosen[i - 1], chosen[(size_t)pick(0, (int)i - 1)]);
+      p.gates = chosen;
+      std::vector<int> sizes;
+      for (int left = (int)chosen.size(); left > 0;) {
+        int sz = pick(1, left);
+        sizes.push_back(sz);
+        left -= sz;
+      }
+      assignGroups(p, sizes);
+    }
   } else {
     fprintf(stderr, "unknown preset %s\n", name.c_str());
     exit(2);
