@@ -37,6 +37,12 @@ def test_gpu_equals_oracle_on_random_shape(p2v, ctx, tmp_path, preset):
     assert np.array_equal(got["eqmask"], want["eqmask"][:m])
     assert np.array_equal(got["status"], want["status"][:m])
     assert np.array_equal(got["qstatus"], want["qstatus"][:m])
-    assert np.array_equal(got["folded"], want["folded"][:, : m * shape.num_queries])
+    # folded evaluations are defined where the reference gets that far (the oracle raises at the first failing check)
+    Q = shape.num_queries
+    for p in range(m):
+        st = int(want["status"][p])
+        if (st & 0xFF) in (0, 3):
+            upto = Q if st == 0 else ((st >> 8) & 0xFF) + 1
+            assert np.array_equal(got["folded"][:, p * Q: p * Q + upto], want["folded"][:, p * Q: p * Q + upto]), p
     assert np.array_equal(got["roots"], oc.fri_roots(blobs[:m]))
     cir.close()
