@@ -858,6 +858,14 @@ static_assert(poseidon_sq_coef_ok(), "double partial rounds: coefficient conditi
 // [15..17] g low, [18..20] e high, [21..23] g high with 1024 e_i + g_i = 2^52 + sigma_i, 1024 e_i - g_i = 2^52 + sigma_{i+3} (sigma = the S seed
 // of the one-level form; e_i has ten fractional bits next to 2^42: exact), then the two parts of the seed of t0 (lane-0 constant of
 // round 5 + 2k).
+// POSEIDON_DBL_ONE_BODY: the last double round (k = 10) hands a FULL constant vector (round 26's) on to the closing rounds; built
+// as a second loop body with every seed loaded (481 instructions, 7.7 KB) it pushes the code that the warps of an SM are spread
+// over — full round, double round, last double round, the Merkle loop — to 35 KB, past the 32 KB instruction cache level.  With
+// this option the seeds of k = 10 carry lane 0's constant only, like every other double round (ONE body, eleven iterations), and
+// lanes 1..11 receive their constants behind the layer with eleven 5-instruction constant additions.
+#ifndef POSEIDON_DBL_ONE_BODY
+#define POSEIDON_DBL_ONE_BODY 1
+#endif
 struct alignas(16) PoseidonRcDbl {
   double v[11][26];
 };
@@ -871,7 +879,12 @@ __host__ __device__ constexpr PoseidonRcDbl poseidon_make_rc_dbl() {
     const int r1 = 5 + 2 * k, r2 = 6 + 2 * k;
     u64 alo[6] = {}, ahi[6] = {}, blo[6] = {}, bhi[6] = {};
     for (int i = 0; i < 6; i++) {
+#if POSEIDON_DBL_ONE_BODY
+      // lane 0's constant only, also for the last pair (the rest of round 26's vector follows behind the layer)
+      u64 a = poseidon_addmod_c(i == 0 ? rce.v[r2][0] : 0, cadj), b = poseidon_addmod_c(0, cadj);
+#else
       u64 a = poseidon_addmod_c(rce.v[r2][i], cadj), b = poseidon_addmod_c(rce.v[r2][i + 6], cadj);
+#endif
       alo[i] = a & 0xFFFFFFFFULL; ahi[i] = a >> 32; blo[i] = b & 0xFFFFFFFFULL; bhi[i] = b >> 32;
       // the unreduced low part of x' is in (-2^34, 2^32) and reaches every output with a coefficient <= 49: lift the low parts by
       // 2^42, take 2^10 off the high parts (same value); a high part below 2^10 is first moved up by p
@@ -912,7 +925,7 @@ __host__ __device__ constexpr bool poseidon_dbl_seed_varies(int k) { return k ==
 constexpr bool poseidon_dbl_static_ok() {
   constexpr PoseidonRcDbl t = poseidon_make_rc_dbl();
   constexpr PoseidonEquivRc rce = poseidon_make_equiv_rc(true);
-  for (int k = 0; k < 10; k++)
+  for (int k = 0; k < (POSEIDON_DBL_ONE_BODY ? 11 : 10); k++)
     for (int j = 0; j < 26; j++)
       if (!poseidon_dbl_seed_varies(j) && t.v[k][j] != t.v[0][j]) return false;
   for (int r = 5; r <= 25; r++)  // the middle rounds (and all but the last target) carry a constant on lane 0 only
@@ -1108,9 +1121,19 @@ __device__ __forceinline__ void poseidon_permute(u64 (&s)[12]) {
     } else {
 #if POSEIDON_MDS_F64 == 4 && POSEIDON_HAVE_DOUBLE_ROUNDS
       // the 22 partial rounds two at a time; the last pair hands the full constant vector on to the closing rounds
+#if POSEIDON_DBL_ONE_BODY
+#pragma unroll 1
+      for (int k = 0; k < 11; k++) poseidon_double_partial_round<true>(s, k);
+      {  // lanes 1..11 of round 26's constants, behind the layer (compile-time values)
+        constexpr PoseidonEquivRc rce = poseidon_make_equiv_rc(true);
+#pragma unroll
+        for (int i = 1; i < 12; i++) s[i] = poseidon_add_rc(s[i], rce.v[26][i]);
+      }
+#else
 #pragma unroll 1
       for (int k = 0; k < 10; k++) poseidon_double_partial_round<true>(s, k);
       poseidon_double_partial_round<false>(s, 10);
+#endif
 #elif POSEIDON_MDS_F64 == 4 && POSEIDON_CRT_LEVEL2 && POSEIDON_EQUIV_RC
       // rounds 4..24 add a constant on lane 0 only (equivalent constants); round 25 hands the full vector on to the closing rounds
 #pragma unroll 1
