@@ -4,6 +4,9 @@ strategies incl. no folding step at all) and 6 real circuits under random FRI pa
 tampered batch and EVERY intermediate of p2v_verify_intermediates (challenges, combined constraint values, quotient-identity
 verdicts, per-query status, folded evaluations, recomputed Merkle roots) must equal the CPU oracle's, bit for bit.  The oracle
 reads the JSON with its own reader; the shapes come from oracle/p2v_prover at test time (tests/random_shapes.py)."""
+import os
+import subprocess
+
 import numpy as np
 import pytest
 
@@ -46,3 +49,9 @@ def test_gpu_equals_oracle_on_random_shape(p2v, ctx, tmp_path, preset):
             assert np.array_equal(got["folded"][:, p * Q: p * Q + upto], want["folded"][:, p * Q: p * Q + upto]), p
     assert np.array_equal(got["roots"], oc.fri_roots(blobs[:m]))
     cir.close()
+    # the reference's driver on this shape (src/testmain.hs:40-63): the C++ host program above the C ABI must print what the
+    # oracle's rendering of `testmain` prints (0 public inputs, 1 or 3 challenge rounds, no folding step ... included)
+    exe = os.path.join(random_shapes.ROOT, "plonky2-verifier_b200", "p2v_testmain")
+    r = subprocess.run([exe, str(tmp_path), preset], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == oc.testmain(fx["proof"])
