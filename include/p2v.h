@@ -217,7 +217,8 @@ int p2v_merkle_verify(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, const ui
 int p2v_merkle_build(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, uint32_t log_n,
                      uint32_t cap_height, uint64_t *digests_out);
 /* Gather n openings from a tree built by p2v_merkle_build: leaves_out SoA [w][n],
- * siblings_out SoA [(log_n-cap_height)*4][n], cap_out [2^cap_height][4]. */
+ * siblings_out SoA [(log_n-cap_height)*4][n], cap_out [2^cap_height][4].  A buffer of zero size (w == 0, or
+ * log_n == cap_height: the cap is the leaf level) may be NULL. */
 int p2v_merkle_open(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, uint32_t log_n,
                     uint32_t cap_height, const uint64_t *digests, const uint32_t *idx, size_t n,
                     uint64_t *leaves_out, uint64_t *siblings_out, uint64_t *cap_out);

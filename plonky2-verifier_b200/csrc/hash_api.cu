@@ -251,9 +251,10 @@ int p2v_merkle_build(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, uint32_t 
 int p2v_merkle_open(p2v_ctx *ctx, const uint64_t *leaves, uint32_t w, uint32_t log_n, uint32_t cap_height,
                     const uint64_t *digests, const uint32_t *idx, size_t n, uint64_t *leaves_out,
                     uint64_t *siblings_out, uint64_t *cap_out) {
-  if (!ctx || !digests || !idx || !leaves_out || !siblings_out || !cap_out || (!leaves && w))
-    return p2v_fail(ctx, P2V_E_INVALID, "p2v_merkle_open: NULL argument");
   if (log_n > 30 || cap_height > log_n) return p2v_fail(ctx, P2V_E_INVALID, "p2v_merkle_open: bad heights");
+  // buffers of zero size may be NULL: no leaves (w == 0), no siblings (the cap is the leaf level)
+  if (!ctx || !digests || !idx || !cap_out || ((!leaves || !leaves_out) && w) || (!siblings_out && log_n > cap_height))
+    return p2v_fail(ctx, P2V_E_INVALID, "p2v_merkle_open: NULL argument");
   P2V_CUDA(ctx, cudaSetDevice(ctx->device));
   size_t n_leaves = (size_t)1 << log_n;
   size_t total = 4 * (((size_t)2 << log_n) - ((size_t)1 << cap_height));
