@@ -127,28 +127,33 @@ struct Cur {
 
 const char *PHANTOM_FIELD = "_phantom: PhantomData<plonky2_field::goldilocks_field::GoldilocksField>";
 
-int numConstraints(const p2v_gate &g) {  // lengths of the committed lists, SURVEY.md App. H
+// A gate string may carry any integer (the reference reads them into 64-bit Ints); the shape record holds ints.  Values beyond
+// INT_MAX are saturated, never truncated, so that validateShape refuses them instead of seeing a small number.
+static int satInt(long long v) { return v > 0x7FFFFFFFLL ? 0x7FFFFFFF : v < -0x7FFFFFFFLL ? -0x7FFFFFFF : (int)v; }
+
+int numConstraints(const p2v_gate &g) {  // lengths of the committed lists, SURVEY.md App. H (64-bit arithmetic, saturated)
+  const long long p0 = g.p0, p1 = g.p1, p2 = g.p2;
   switch (g.kind) {
-    case P2V_GATE_ARITHMETIC: return g.p0;
-    case P2V_GATE_ARITHMETIC_EXT: return 2 * g.p0;
-    case P2V_GATE_BASE_SUM: return 1 + g.p0;
+    case P2V_GATE_ARITHMETIC: return satInt(p0);
+    case P2V_GATE_ARITHMETIC_EXT: return satInt(2 * p0);
+    case P2V_GATE_BASE_SUM: return satInt(1 + p0);
     case P2V_GATE_COSET_INTERP: {
-      if (g.p1 < 2) return 0;
-      int n_points = 1 << g.p0, d = g.p1;
-      int n_int = (n_points - 2) / (d - 1);
-      int chunks = 1 + (n_points > d ? (n_points - d + d - 2) / (d - 1) : 0);
-      int wchunks = 1 + (g.weights_len > d ? (g.weights_len - d + d - 2) / (d - 1) : 0);
-      int nstuff = std::min(std::min(chunks, wchunks), n_int + 1);
-      return 2 + 4 * (nstuff - 1) + 2;
+      if (p1 < 2 || p0 < 0 || p0 > 30) return 0;  // refused by validateShape / checkShapeSupported
+      long long n_points = 1LL << p0, d = p1;
+      long long n_int = (n_points - 2) / (d - 1);
+      long long chunks = 1 + (n_points > d ? (n_points - d + d - 2) / (d - 1) : 0);
+      long long wchunks = 1 + (g.weights_len > d ? (g.weights_len - d + d - 2) / (d - 1) : 0);
+      long long nstuff = std::min(std::min(chunks, wchunks), n_int + 1);
+      return satInt(2 + 4 * (nstuff - 1) + 2);
     }
-    case P2V_GATE_CONSTANT: return g.p0;
-    case P2V_GATE_EXPONENTIATION: return g.p0 + 1;
-    case P2V_GATE_MUL_EXT: return 2 * g.p0;
+    case P2V_GATE_CONSTANT: return satInt(p0);
+    case P2V_GATE_EXPONENTIATION: return satInt(p0 + 1);
+    case P2V_GATE_MUL_EXT: return satInt(2 * p0);
     case P2V_GATE_PUBLIC_INPUT: return 4;
     case P2V_GATE_POSEIDON: return 123;
     case P2V_GATE_POSEIDON_MDS: return 24;
-    case P2V_GATE_RANDOM_ACCESS: return g.p1 * (g.p0 + 2) + g.p2;
-    case P2V_GATE_REDUCING: case P2V_GATE_REDUCING_EXT: return 2 * g.p0;
+    case P2V_GATE_RANDOM_ACCESS: return satInt(p1 * (p0 + 2) + p2);
+    case P2V_GATE_REDUCING: case P2V_GATE_REDUCING_EXT: return satInt(2 * p0);
     default: return 0;
   }
 }
@@ -159,16 +164,16 @@ bool parseAlt(int alt, Cur &c, p2v_gate &g, uint64_t *weights) {
   switch (alt) {
     case 0:  // arithmeticGateP (withEOF)
       if (!c.structOpen("ArithmeticGate") || !c.keyInt("num_ops", a) || !c.structClose() || !c.eof()) return false;
-      g.kind = P2V_GATE_ARITHMETIC; g.p0 = (int)a; return true;
+      g.kind = P2V_GATE_ARITHMETIC; g.p0 = satInt(a); return true;
     case 1:  // arithmeticExtensionGateP (withEOF)
       if (!c.structOpen("ArithmeticExtensionGate") || !c.keyInt("num_ops", a) || !c.structClose() || !c.eof()) return false;
-      g.kind = P2V_GATE_ARITHMETIC_EXT; g.p0 = (int)a; return true;
+      g.kind = P2V_GATE_ARITHMETIC_EXT; g.p0 = satInt(a); return true;
     case 2:  // baseSumGateP (withEOF): "BaseSumGate { num_limbs: 63 } + Base: 2"
       if (!c.structOpen("BaseSumGate") || !c.keyInt("num_limbs", a) || !c.structClose()) return false;
       if (!c.chr('+')) return false;
       c.spaces();
       if (!c.keyInt("Base", b) || !c.eof()) return false;
-      g.kind = P2V_GATE_BASE_SUM; g.p0 = (int)a; g.p1 = (int)b; return true;
+      g.kind = P2V_GATE_BASE_SUM; g.p0 = satInt(a); g.p1 = satInt(b); return true;
     case 3: {  // cosetInterpolationGateP (withEOF)
       if (!c.structOpen("CosetInterpolationGate")) return false;
       if (!c.keyInt("subgroup_bits", a) || !c.commaP() || !c.keyInt("degree", b) || !c.commaP()) return false;
@@ -186,29 +191,29 @@ bool parseAlt(int alt, Cur &c, p2v_gate &g, uint64_t *weights) {
       c.spaces();
       if (!c.structClose() || !c.str("<D=2>") || !c.eof()) return false;
       if (overflow) throw JsonError("CosetInterpolationGate: more than P2V_MAX_WEIGHTS barycentric weights");
-      g.kind = P2V_GATE_COSET_INTERP; g.p0 = (int)a; g.p1 = (int)b; g.weights_len = nw; return true;
+      g.kind = P2V_GATE_COSET_INTERP; g.p0 = satInt(a); g.p1 = satInt(b); g.weights_len = nw; return true;
     }
     case 4:  // constantGateP (no EOF check in the reference)
       if (!c.structOpen("ConstantGate") || !c.keyInt("num_consts", a) || !c.structClose()) return false;
-      g.kind = P2V_GATE_CONSTANT; g.p0 = (int)a; return true;
+      g.kind = P2V_GATE_CONSTANT; g.p0 = satInt(a); return true;
     case 5:
       if (!c.structOpen("ExponentiationGate") || !c.keyInt("num_power_bits", a) || !c.structClose()) return false;
-      g.kind = P2V_GATE_EXPONENTIATION; g.p0 = (int)a; return true;
+      g.kind = P2V_GATE_EXPONENTIATION; g.p0 = satInt(a); return true;
     case 6: {  // lookupGateP
       if (!c.structOpen("LookupGate") || !c.keyInt("num_slots", a) || !c.commaP()) return false;
       auto byte = [&](Cur &cc) { long long v; return cc.intP(v); };
       if (!c.keyList("lut_hash", byte) || !c.structClose()) return false;
-      g.kind = P2V_GATE_LOOKUP; g.p0 = (int)a; return true;
+      g.kind = P2V_GATE_LOOKUP; g.p0 = satInt(a); return true;
     }
     case 7: {  // lookupTableGateP
       if (!c.structOpen("LookupTableGate") || !c.keyInt("num_slots", a) || !c.commaP()) return false;
       auto byte = [&](Cur &cc) { long long v; return cc.intP(v); };
       if (!c.keyList("lut_hash", byte) || !c.commaP() || !c.keyInt("last_lut_row", b) || !c.structClose()) return false;
-      g.kind = P2V_GATE_LOOKUP_TABLE; g.p0 = (int)a; g.p1 = (int)b; return true;
+      g.kind = P2V_GATE_LOOKUP_TABLE; g.p0 = satInt(a); g.p1 = satInt(b); return true;
     }
     case 8:
       if (!c.structOpen("MulExtensionGate") || !c.keyInt("num_ops", a) || !c.structClose()) return false;
-      g.kind = P2V_GATE_MUL_EXT; g.p0 = (int)a; return true;
+      g.kind = P2V_GATE_MUL_EXT; g.p0 = satInt(a); return true;
     case 9:  // noopGateP = string "NoopGate"
       if (!c.str("NoopGate")) return false;
       g.kind = P2V_GATE_NOOP; return true;
@@ -217,17 +222,17 @@ bool parseAlt(int alt, Cur &c, p2v_gate &g, uint64_t *weights) {
       g.kind = P2V_GATE_PUBLIC_INPUT; return true;
     case 11:  // poseidonGateP (eof)
       if (!c.str("PoseidonGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=") || !c.intP(a) || !c.str(">") || !c.eof()) return false;
-      g.kind = P2V_GATE_POSEIDON; g.p0 = (int)a; return true;
+      g.kind = P2V_GATE_POSEIDON; g.p0 = satInt(a); return true;
     case 12:
       if (!c.str("PoseidonMdsGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=") || !c.intP(a) || !c.str(">") || !c.eof()) return false;
-      g.kind = P2V_GATE_POSEIDON_MDS; g.p0 = (int)a; return true;
+      g.kind = P2V_GATE_POSEIDON_MDS; g.p0 = satInt(a); return true;
     case 13:  // randomAccessGateP
       if (!c.structOpen("RandomAccessGate")) return false;
       if (!c.keyInt("bits", a) || !c.commaP() || !c.keyInt("num_copies", b) || !c.commaP() || !c.keyInt("num_extra_constants", d)) return false;
       if (!c.commaP() || !c.str(PHANTOM_FIELD)) return false;
       c.spaces();
       if (!c.structClose() || !c.str("<D=2>")) return false;
-      g.kind = P2V_GATE_RANDOM_ACCESS; g.p0 = (int)a; g.p1 = (int)b; g.p2 = (int)d; return true;
+      g.kind = P2V_GATE_RANDOM_ACCESS; g.p0 = satInt(a); g.p1 = satInt(b); g.p2 = satInt(d); return true;
     case 14:  // reducingGateP: the struct, then `optional (string "<D=2>")`
       if (!c.structOpen("ReducingGate") || !c.keyInt("num_coeffs", a)) return false;
       {  // `optional $ string "<D=2>"` sits INSIDE rustStructP's user parser in the reference (:230-234)
@@ -235,7 +240,7 @@ bool parseAlt(int alt, Cur &c, p2v_gate &g, uint64_t *weights) {
         if (!c.str("<D=2>")) { if (c.pos != save) return false; }
       }
       if (!c.structClose()) return false;
-      g.kind = P2V_GATE_REDUCING; g.p0 = (int)a; return true;
+      g.kind = P2V_GATE_REDUCING; g.p0 = satInt(a); return true;
     case 15:
       if (!c.structOpen("ReducingExtensionGate") || !c.keyInt("num_coeffs", a)) return false;
       {
@@ -243,7 +248,7 @@ bool parseAlt(int alt, Cur &c, p2v_gate &g, uint64_t *weights) {
         if (!c.str("<D=2>")) { if (c.pos != save) return false; }
       }
       if (!c.structClose()) return false;
-      g.kind = P2V_GATE_REDUCING_EXT; g.p0 = (int)a; return true;
+      g.kind = P2V_GATE_REDUCING_EXT; g.p0 = satInt(a); return true;
   }
   return false;
 }

@@ -40,27 +40,33 @@ int checkShapeSupported(p2v_ctx *ctx, const p2v_shape &s) {
       case P2V_GATE_RANDOM_ACCESS:
         if (g.p0 < 0 || g.p0 > 7) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "RandomAccessGate: bits out of range");
         break;
+      case P2V_GATE_BASE_SUM:
+        // the limb range check is a product over the base (Gate/Constraints.hs: prod (limb - k), k < B): B per limb and proof
+        if (g.p1 < 0 || g.p1 > 256) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "BaseSumGate: base above 256");
+        break;
       default: break;
     }
   }
   // every wire / constant index a gate touches must exist (Array `!` raises in the reference)
-  auto need = [&](int k) -> int {
+  // (64-bit: the parameters are bounded by validateShape, their products are not — num_copies = 2^30 would wrap an int)
+  auto need = [&](int k) -> long long {
     const p2v_gate &g = s.gates[k];
+    const long long p0 = g.p0, p1 = g.p1, p2 = g.p2;
     switch (g.kind) {
-      case P2V_GATE_ARITHMETIC: return 4 * g.p0;
-      case P2V_GATE_ARITHMETIC_EXT: return 8 * g.p0;
-      case P2V_GATE_MUL_EXT: return 6 * g.p0;
-      case P2V_GATE_BASE_SUM: return 1 + g.p0;
-      case P2V_GATE_CONSTANT: return g.p0;
+      case P2V_GATE_ARITHMETIC: return 4 * p0;
+      case P2V_GATE_ARITHMETIC_EXT: return 8 * p0;
+      case P2V_GATE_MUL_EXT: return 6 * p0;
+      case P2V_GATE_BASE_SUM: return 1 + p0;
+      case P2V_GATE_CONSTANT: return p0;
       case P2V_GATE_PUBLIC_INPUT: return 4;
-      case P2V_GATE_EXPONENTIATION: return 2 * g.p0 + 2;
+      case P2V_GATE_EXPONENTIATION: return 2 * p0 + 2;
       case P2V_GATE_POSEIDON: return 135;
       case P2V_GATE_POSEIDON_MDS: return 48;
-      case P2V_GATE_RANDOM_ACCESS: return ((2 + (1 << g.p0)) * g.p1 + g.p2 + g.p0 * g.p1);
-      case P2V_GATE_REDUCING: return g.p0 ? 3 * g.p0 + 4 : 0;
-      case P2V_GATE_REDUCING_EXT: return g.p0 ? 4 * g.p0 + 4 : 0;
+      case P2V_GATE_RANDOM_ACCESS: return ((2 + (1LL << p0)) * p1 + p2 + p0 * p1);
+      case P2V_GATE_REDUCING: return p0 ? 3 * p0 + 4 : 0;
+      case P2V_GATE_REDUCING_EXT: return p0 ? 4 * p0 + 4 : 0;
       case P2V_GATE_COSET_INTERP: {
-        int np = 1 << g.p0, ni = (np - 2) / (g.p1 - 1);
+        long long np = 1LL << p0, ni = (np - 2) / (p1 - 1);
         return 1 + 2 * (np + 2) + 4 * ni + 2;
       }
       default: return 0;

@@ -243,3 +243,29 @@ def test_a_group_that_cannot_run_does_not_stop_the_others(p2v, ctx, orc):
         foreign.close()
     finally:
         other.close()
+
+
+@pytest.mark.parametrize("gate", [
+    "RandomAccessGate { bits: 7, num_copies: 1073741824, num_extra_constants: 0, _phantom: PhantomData<plonky2_field::goldilocks_field::GoldilocksField> }<D=2>",
+    "RandomAccessGate { bits: 1, num_copies: 4294967297, num_extra_constants: 0, _phantom: PhantomData<plonky2_field::goldilocks_field::GoldilocksField> }<D=2>",
+    "BaseSumGate { num_limbs: 3 } + Base: 1000000",
+    "ArithmeticGate { num_ops: 4294967300 }",
+    "ExponentiationGate { num_power_bits: 10 }",
+])
+def test_hostile_gate_parameters_are_refused(p2v, ctx, gate):
+    """A circuit description whose gate parameters would wrap 32-bit index arithmetic (num_copies = 2^30 makes the wire count of a
+    RandomAccessGate 130 * 2^30), truncate (2^32 + 1 read as 1), run a per-limb product over a huge base, or simply need more wires
+    than the circuit has, is refused when the circuit is created — never handed to a kernel."""
+    import json
+
+    common = json.loads(fixtures.read("small6", "common"))
+    common["gates"][2] = gate
+    try:
+        shape = p2v.parse_common(json.dumps(common))
+    except p2v.P2VError as e:
+        assert e.code in (-5, -6)
+        return
+    lay = p2v.shape_layout(shape)
+    with pytest.raises(p2v.P2VError) as ei:
+        p2v.Circuit(ctx, shape, np.zeros(lay.vkey_words, dtype=np.uint64))
+    assert ei.value.code in (-5, -6), ei.value

@@ -372,3 +372,25 @@ def test_fast_scanner_leaves_leading_zeros_to_the_tape_reader(p2v):
         p2v.parse_proof(bad, shape)
     assert e.value.code == -4
 
+
+
+def test_host_parsers_under_asan_and_ubsan(tmp_path):
+    """tools/fuzz_host_asan.cpp: the C++ host parsers compiled with -fsanitize=address,undefined and fed mutated common / vkey /
+    proof / gate texts of seven fixtures.  Found (fourth session): signed overflow in the constraint count of a gate with a huge
+    parameter, and parameters above INT_MAX truncated instead of refused."""
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    exe = str(tmp_path / "fuzz_host")
+    cc = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-I", os.path.join(root, "include"),
+                         os.path.join(root, "tools", "fuzz_host_asan.cpp"), os.path.join(root, "plonky2-verifier_b200", "csrc", "host", "parse.cpp"),
+                         "-o", exe, "-lpthread"], capture_output=True, text=True)
+    if cc.returncode != 0 and "sanitize" in cc.stderr:
+        pytest.skip("this g++ has no sanitizer runtime")
+    assert cc.returncode == 0, cc.stderr[-2000:]
+    run = subprocess.run([exe, os.path.join(root, "tests", "golden"), "600"], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]
+    assert "proof ok/bad" in run.stdout
