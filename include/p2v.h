@@ -57,6 +57,7 @@ extern "C" {
 #define P2V_MAX_STEPS 16
 #define P2V_MAX_LUTS 16
 #define P2V_MAX_WEIGHTS 256
+#define P2V_MAX_CHALLENGES 4 /* num_challenges the kernels keep in registers (Plonky2's configurations use 2 or 3) */
 
 /* Gate kinds: the constructors of `data Gate`, Gate/Base.hs:27-45. */
 enum p2v_gate_kind {
@@ -230,6 +231,11 @@ void p2v_shape_free(p2v_shape *shape);
 /* `recognizeGate`, Gate/Parser.hs:107.  weights: out array of P2V_MAX_WEIGHTS. */
 int p2v_parse_gate(const char *str, size_t len, p2v_gate *out, uint64_t *weights);
 int p2v_shape_layout(const p2v_shape *shape, p2v_layout *out);
+/* Vet a circuit description without a GPU: every integer that enters an offset, a loop bound or a shift is in range, and every
+ * gate is one the kernels implement with parameters that fit the circuit (the reference's `error` / array-index sites:
+ * Gate/Constraints.hs:93-108, Gate/Selector.hs:85).  P2V_OK, or P2V_E_SHAPE / P2V_E_UNSUPPORTED with the reason in
+ * p2v_last_error(NULL).  p2v_circuit_create runs the same check. */
+int p2v_shape_check(const p2v_shape *shape);
 int p2v_challenges_words(const p2v_shape *shape);
 /* `FromJSON VerifierOnlyCircuitData`: out[vkey_words] = cap ++ circuit_digest. */
 int p2v_parse_vkey(const char *json, size_t len, const p2v_shape *shape, uint64_t *out);

@@ -133,6 +133,7 @@ def lib():
         "p2v_shape_free": (None, [C.POINTER(Shape)]),
         "p2v_parse_gate": (C.c_int, [C.c_char_p, sz, C.POINTER(Gate), u64p]),
         "p2v_shape_layout": (C.c_int, [C.POINTER(Shape), C.POINTER(Layout)]),
+        "p2v_shape_check": (C.c_int, [C.POINTER(Shape)]),
         "p2v_challenges_words": (C.c_int, [C.POINTER(Shape)]),
         "p2v_parse_vkey": (C.c_int, [C.c_char_p, sz, C.POINTER(Shape), u64p]),
         "p2v_parse_proof": (C.c_int, [C.c_char_p, sz, C.POINTER(Shape), u64p]),
@@ -175,7 +176,7 @@ EXPORTED_SYMBOLS = [
     "p2v_abi_version", "p2v_ctx_create", "p2v_ctx_destroy", "p2v_last_error", "p2v_ctx_stream", "p2v_ctx_sync",
     "p2v_ctx_launch_count", "p2v_host_alloc", "p2v_host_free", "p2v_poseidon_permute", "p2v_hash_leaves",
     "p2v_compress", "p2v_merkle_verify", "p2v_merkle_build", "p2v_merkle_open", "p2v_parse_common",
-    "p2v_shape_free", "p2v_parse_gate", "p2v_shape_layout", "p2v_challenges_words", "p2v_parse_vkey",
+    "p2v_shape_free", "p2v_parse_gate", "p2v_shape_layout", "p2v_shape_check", "p2v_challenges_words", "p2v_parse_vkey",
     "p2v_parse_proof", "p2v_parse_proofs", "p2v_circuit_create", "p2v_circuit_destroy", "p2v_challenges", "p2v_constraints",
     "p2v_fri", "p2v_verify_batch", "p2v_verify_groups", "p2v_ctx_set_chunk", "p2v_ctx_set_pipeline", "p2v_synth_batch", "p2v_int_pipe_peak", "p2v_ctx_last_ms",
     "p2v_shard_slice_len", "p2v_shard_bounds", "p2v_nccl_unique_id", "p2v_nccl_init", "p2v_nccl_attach", "p2v_nccl_finalize",
@@ -236,6 +237,13 @@ def shape_layout(shape):
     if rc:
         raise P2VError(rc, lib().p2v_last_error(None).decode())
     return lay
+
+
+def shape_check(shape):
+    """p2v_shape_check: vet a circuit description without a GPU (raises P2VError with the reason)."""
+    rc = lib().p2v_shape_check(C.byref(shape))
+    if rc:
+        raise P2VError(rc, lib().p2v_last_error(None).decode())
 
 
 def challenges_words(shape):

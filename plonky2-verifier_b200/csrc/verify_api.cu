@@ -21,69 +21,6 @@ namespace {
 
 using namespace p2vhost;
 
-int checkShapeSupported(p2v_ctx *ctx, const p2v_shape &s) {
-  if (s.num_challenges > P2V_MAX_CHALLENGES)
-    return p2v_fail(ctx, P2V_E_UNSUPPORTED, "num_challenges > 4 is not supported");
-  for (int k = 0; k < s.num_gates; k++) {
-    const p2v_gate &g = s.gates[k];
-    switch (g.kind) {
-      case P2V_GATE_UNKNOWN:
-        return p2v_fail(ctx, P2V_E_UNSUPPORTED, "gateConstraints: unknown gate (Gate/Constraints.hs:108)");
-      case P2V_GATE_POSEIDON:
-      case P2V_GATE_POSEIDON_MDS:
-        if (g.p0 != 12) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "gateConstraints/PoseidonGate: unsupported width (Gate/Constraints.hs:93,97)");
-        break;
-      case P2V_GATE_COSET_INTERP:
-        if (g.p0 < 1 || g.p0 > 5 || g.p1 < 2 || g.weights_len != (1 << g.p0))
-          return p2v_fail(ctx, P2V_E_UNSUPPORTED, "CosetInterpolationGate: need 2^subgroup_bits weights, degree >= 2, subgroup_bits <= 5");
-        break;
-      case P2V_GATE_RANDOM_ACCESS:
-        if (g.p0 < 0 || g.p0 > 7) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "RandomAccessGate: bits out of range");
-        break;
-      case P2V_GATE_BASE_SUM:
-        // the limb range check is a product over the base (Gate/Constraints.hs: prod (limb - k), k < B): B per limb and proof
-        if (g.p1 < 0 || g.p1 > 256) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "BaseSumGate: base above 256");
-        break;
-      default: break;
-    }
-  }
-  // every wire / constant index a gate touches must exist (Array `!` raises in the reference)
-  // (64-bit: the parameters are bounded by validateShape, their products are not — num_copies = 2^30 would wrap an int)
-  auto need = [&](int k) -> long long {
-    const p2v_gate &g = s.gates[k];
-    const long long p0 = g.p0, p1 = g.p1, p2 = g.p2;
-    switch (g.kind) {
-      case P2V_GATE_ARITHMETIC: return 4 * p0;
-      case P2V_GATE_ARITHMETIC_EXT: return 8 * p0;
-      case P2V_GATE_MUL_EXT: return 6 * p0;
-      case P2V_GATE_BASE_SUM: return 1 + p0;
-      case P2V_GATE_CONSTANT: return p0;
-      case P2V_GATE_PUBLIC_INPUT: return 4;
-      case P2V_GATE_EXPONENTIATION: return 2 * p0 + 2;
-      case P2V_GATE_POSEIDON: return 135;
-      case P2V_GATE_POSEIDON_MDS: return 48;
-      case P2V_GATE_RANDOM_ACCESS: return ((2 + (1LL << p0)) * p1 + p2 + p0 * p1);
-      case P2V_GATE_REDUCING: return p0 ? 3 * p0 + 4 : 0;
-      case P2V_GATE_REDUCING_EXT: return p0 ? 4 * p0 + 4 : 0;
-      case P2V_GATE_COSET_INTERP: {
-        long long np = 1LL << p0, ni = (np - 2) / (p1 - 1);
-        return 1 + 2 * (np + 2) + 4 * ni + 2;
-      }
-      default: return 0;
-    }
-  };
-  for (int k = 0; k < s.num_gates; k++) {
-    if (need(k) > s.num_wires) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "a gate reads a wire beyond num_wires (array index error in the reference)");
-    const p2v_gate &g = s.gates[k];
-    int nconst = g.kind == P2V_GATE_CONSTANT ? g.p0 : g.kind == P2V_GATE_RANDOM_ACCESS ? g.p2 : (g.kind == P2V_GATE_ARITHMETIC || g.kind == P2V_GATE_ARITHMETIC_EXT) ? 2 : g.kind == P2V_GATE_MUL_EXT ? 1 : 0;
-    if (g.p0 > 0 && nconst > s.num_gate_constants) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "a gate reads a constant beyond config.num_constants");
-  }
-  if (s.num_luts > 0 && s.num_lookup_polys < 2) return p2v_fail(ctx, P2V_E_UNSUPPORTED, "lookup tables need at least 2 lookup polynomials");
-  if (s.num_luts > 0 && (s.num_routed_wires / 3 < 1 || 3 * (s.num_routed_wires / 3) > s.num_wires))
-    return p2v_fail(ctx, P2V_E_UNSUPPORTED, "lookup slots exceed the wires");
-  return P2V_OK;
-}
-
 void buildTranscript(DevCircuit &d) {
   const p2v_layout &L = d.L;
   int n = 0;
@@ -731,8 +668,8 @@ int p2v_ctx_last_ms(p2v_ctx *ctx, const char *section, float *ms) {
 int p2v_circuit_create(p2v_ctx *ctx, const p2v_shape *shape, const uint64_t *vkey, p2v_circuit **out) {
   if (!ctx || !shape || !vkey || !out) return p2v_fail(ctx, P2V_E_INVALID, "p2v_circuit_create: NULL argument");
   P2V_CUDA(ctx, cudaSetDevice(ctx->device));
-  int rc = checkShapeSupported(ctx, *shape);
-  if (rc) return rc;
+  int rc = p2v_shape_check(shape);  // host-side (csrc/host/parse.cpp): ranges + what the kernels implement
+  if (rc) return p2v_fail(ctx, rc, p2v_tls_error);
   p2v_layout L;
   if ((rc = p2v_shape_layout(shape, &L))) {
     ctx->err = p2v_tls_error;

@@ -13,7 +13,6 @@
 #include "poseidon.cuh"
 #include "../../include/p2v.h"
 
-#define P2V_MAX_CHALLENGES 4
 #define P2V_MAX_TOPS 64
 
 // One operation of the transcript (Challenge/Verifier.hs:73-94, Challenge/FRI.hs:73-97)

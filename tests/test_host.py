@@ -394,3 +394,26 @@ def test_host_parsers_under_asan_and_ubsan(tmp_path):
     run = subprocess.run([exe, os.path.join(root, "tests", "golden"), "600"], capture_output=True, text=True, timeout=300)
     assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]
     assert "proof ok/bad" in run.stdout
+
+
+def test_hostile_circuit_descriptions_under_asan(tmp_path):
+    """oracle/fuzz_shapes.cpp: mutated `*_common.json` texts (structural numbers replaced by boundary values, gate strings dropped or
+    duplicated) that the host parser accepts AND p2v_shape_check passes are verified by the CPU oracle compiled with ASAN, UBSAN and
+    _GLIBCXX_ASSERTIONS, with a blob of the shape's size.  The oracle indexes where the reference indexes, so a report, an oracle
+    exception or a run-away loop means the shape check lets through a circuit a kernel would misbehave on."""
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    exe = str(tmp_path / "fuzz_shapes")
+    cc = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-D_GLIBCXX_ASSERTIONS",
+                         "-I", os.path.join(root, "include"), "-I", os.path.join(root, "oracle"), os.path.join(root, "oracle", "fuzz_shapes.cpp"),
+                         os.path.join(root, "plonky2-verifier_b200", "csrc", "host", "parse.cpp"), "-o", exe, "-lpthread"], capture_output=True, text=True)
+    if cc.returncode != 0 and "sanitize" in cc.stderr:
+        pytest.skip("this g++ has no sanitizer runtime")
+    assert cc.returncode == 0, cc.stderr[-2000:]
+    run = subprocess.run([exe, os.path.join(root, "tests", "golden"), "1200"], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]
+    assert "oracle exceptions 0" in run.stdout, run.stdout + run.stderr[-2000:]
