@@ -417,3 +417,26 @@ def test_hostile_circuit_descriptions_under_asan(tmp_path):
     run = subprocess.run([exe, os.path.join(root, "tests", "golden"), "1200"], capture_output=True, text=True, timeout=600)
     assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]
     assert "oracle exceptions 0" in run.stdout, run.stdout + run.stderr[-2000:]
+
+
+def test_shape_check_without_a_gpu():
+    """p2v_shape_check vets a circuit description on the host: every bundled circuit passes, hostile gate parameters do not."""
+    import plonky2_verifier_b200 as p2v
+
+    for name in fixtures.ACCEPTING:
+        p2v.shape_check(fixtures.load(name)[0])
+    hostile = [
+        "RandomAccessGate { bits: 7, num_copies: 1073741824, num_extra_constants: 0, _phantom: PhantomData<plonky2_field::goldilocks_field::GoldilocksField> }<D=2>",
+        "RandomAccessGate { bits: 1, num_copies: 4294967297, num_extra_constants: 0, _phantom: PhantomData<plonky2_field::goldilocks_field::GoldilocksField> }<D=2>",
+        "BaseSumGate { num_limbs: 3 } + Base: 1000000",
+        "ArithmeticGate { num_ops: 4294967300 }",
+        "ExponentiationGate { num_power_bits: 10 }",   # needs 22 wires, the circuit has 20
+        "PoseidonGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>",  # needs 135 wires
+        "SomeFutureGate { x: 1 }",                      # UnknownGate: `error` in gateConstraints (Gate/Constraints.hs:108)
+    ]
+    for gate in hostile:
+        common = json.loads(fixtures.read("small6", "common"))
+        common["gates"][2] = gate
+        with pytest.raises(p2v.P2VError) as ei:
+            p2v.shape_check(p2v.parse_common(json.dumps(common)))
+        assert ei.value.code in (-5, -6), (gate, ei.value)
